@@ -1,0 +1,154 @@
+/* ngp.h -- C ABI of libngp.so: the B200-native population-evaluation hot path of
+ * n00b001/neuro-genetic-pong-self-play.
+ *
+ * The reference has no FFI layer; its operator surface is the DEAP toolbox plus three
+ * duck-typed objects.  Each entry point below names the reference
+ * interface it replaces (file:line in the reference tree).
+ *
+ * Conventions: every function returns 0 on success or a negative ngp_status;
+ * ngp_last_error() gives the message for the calling thread.  All pointers are caller
+ * owned.  Pointers documented "device" are CUDA device pointers on the handle's GPU,
+ * "host" are ordinary host pointers (the *_host entry points stage through pinned memory
+ * and include the copies).  `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream).  One handle per GPU; a handle is not thread-safe; distinct handles are
+ * independent.  No torch types appear here.
+ */
+#ifndef NGP_H
+#define NGP_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGP_MAX_LAYERS 8
+#define NGP_FRAME_ROWS 210
+#define NGP_FRAME_COLS 160
+#define NGP_RAM_BYTES 128
+#define NGP_GAMES_TO_PLAY 6          /* config.py:46 */
+
+typedef enum {
+    NGP_OK = 0,
+    NGP_ERR_INVALID = -1,            /* bad argument */
+    NGP_ERR_CUDA = -2,               /* CUDA runtime error (message has the detail) */
+    NGP_ERR_UNSUPPORTED = -3,        /* e.g. network too wide for the fused rollout */
+    NGP_ERR_EMULATOR = -4            /* an environment hit an illegal opcode / decimal mode */
+} ngp_status;
+
+/* actions as the reference's model.run() returns them: [0,0] [1,0] [0,1] */
+enum { NGP_ACT_NONE = 0, NGP_ACT_UP = 1, NGP_ACT_DOWN = 2 };
+/* retro save states used by the reference: default ('Start', 1 player vs the cartridge
+ * robot, main.py:40) and 'Start.2P' (main.py:21,51) */
+enum { NGP_STATE_START_1P = 0, NGP_STATE_START_2P = 1 };
+/* opponent schedule of one evaluation */
+enum {
+    NGP_SCHEDULE_REFERENCE = 0,      /* main.py:33-58: bot, robot, score-bot, 3 x hall of fame */
+    NGP_SCHEDULE_ROUND_ROBIN = 1     /* genome i (right) vs genome (i+k) mod N (left), k=1..games */
+};
+
+/* Mirror of /root/reference/config.py (names kept) + network shape + schedule. */
+typedef struct {
+    int32_t n_layers;                        /* len(NETWORK_SHAPE), config.py:30-32 */
+    int32_t nodes[NGP_MAX_LAYERS];           /* NETWORK_SHAPE */
+    int32_t bias;                            /* BIAS, config.py:34 */
+    int32_t games_to_play;                   /* GAMES_TO_PLAY, config.py:46 (<= 6 for the reference schedule) */
+    int32_t win_score;                       /* WIN_SCORE, config.py:53 */
+    int32_t timeout_thresh;                  /* TIMEOUT_THRESH, config.py:28 */
+    int32_t schedule;                        /* NGP_SCHEDULE_* */
+    int32_t max_frames;                      /* 0 = unlimited; hard stop per episode (tests) */
+    float time_scaler;                       /* TIME_SCALER, config.py:54 */
+    float scaled_paddle_height;              /* SCALED_PADDLE_HEIGHT, config.py:10 */
+    uint8_t ball_colour[3];                  /* BALL_COLOUR, config.py:4 */
+    uint8_t left_colour[3];                  /* LEFT_GUY_COLOUR, config.py:5 */
+    uint8_t right_colour[3];                 /* RIGHT_GUY_COLOUR, config.py:6 */
+    uint8_t pad_[3];
+    /* GA rates, config.py:36-43, 49-50 */
+    float cxpb, cx_alpha, mutpb, mut_mu, mut_sigma, mut_indpb;
+    int32_t tournament_size;                 /* TOURNAMENT_SIZE = POPULATION_SIZE // 4 */
+} ngp_config;
+
+typedef struct ngp_handle ngp_handle;
+
+/* Fills cfg with config.py's defaults for a population of `population` genomes. */
+void ngp_default_config(ngp_config *cfg, int32_t population);
+const char *ngp_last_error(void);
+const char *ngp_version(void);
+
+/* rom: the 2048-byte cartridge image (host).  Builds the power-on -> 'Start'/'Start.2P'
+ * snapshots on the device with the CUDA core itself. */
+int ngp_create(const ngp_config *cfg, const uint8_t *rom, int32_t device, ngp_handle **out);
+int ngp_destroy(ngp_handle *h);
+int32_t ngp_gene_size(const ngp_handle *h);                 /* utils.calculate_gene_size, utils.py:128-136 */
+
+/* ---- K1: batched Atari 2600 core, explicit-action stepping (verify / stepwise mode) ----
+ * Replaces retro.make + env.reset (main.py:21,40,51,56) and env.step (main.py:77). */
+int ngp_env_reset(ngp_handle *h, int32_t n_envs, int32_t state_id, void *stream);
+/* actions: device u8[n_envs][16] in gym-retro button order (config.py:15-23).  Outputs
+ * (device, any may be NULL): ram u8[n][128]; frames u8[n][210][160][3] RGB (obs.npy layout);
+ * loc f32[n][3][2] + valid u8[n][3]: the fused find_stuff result for the same frame;
+ * regs u8[n][8] = A X Y SP P PCL PCH err. */
+int ngp_env_step(ngp_handle *h, const uint8_t *actions, uint8_t *ram, uint8_t *frames,
+                 float *loc, uint8_t *valid, uint8_t *regs, void *stream);
+/* debug/parity: TIA digest u32[n][8] (collision latches, object positions, paddle charges) */
+int ngp_env_digest(ngp_handle *h, uint32_t *digest, void *stream);
+
+/* ---- K2: frame -> observation.  Replaces utils.find_stuff / get_rect_quickly
+ * (utils.py:14-19, 60-68).  frames: device u8[n][210][160][3]; loc f32[n][3][2] (row, col in
+ * cropped coordinates; ball, left, right); valid u8[n][3] (0 == the reference's None). */
+int ngp_find_stuff(ngp_handle *h, const uint8_t *frames, int32_t n, float *loc, uint8_t *valid, void *stream);
+
+/* ---- K3: per-genome grouped MLP forward.  Replaces NeuralNetwork.__init__/populate_weights/
+ * run (numpy_nn.py:35-69, 120-137).  genomes f32[n_genomes][G] (reference gene order, bias
+ * weight = last column), x f32[n_genomes][envs][n_in]; act u8[n_genomes][envs] (NGP_ACT_UP/DOWN),
+ * out (may be NULL) f32[n_genomes][envs][n_out]. */
+int ngp_mlp_forward(ngp_handle *h, const float *genomes, const float *x, int32_t n_genomes, int32_t envs,
+                    uint8_t *act, float *out, void *stream);
+
+/* ---- fused hot path: population genomes in -> fitness out.  Replaces
+ * toolbox.map(toolbox.evaluate, population) (ga.py:83, main.py:28-66, main.py:69-154).
+ * genomes: device f32[n][G].  hof_genomes f32[n_hof][G], hof_fitness f64[n_hof] (device; may be
+ * NULL with n_hof = 0).  hof_pick: optional device i32[n][3] (injected hall-of-fame choices for
+ * games 3..5; NULL = drawn from Philox(seed, generation)).  Outputs (device): fitness f64[n];
+ * rewards f64[n][games] (may be NULL); frames i32[n][games] (may be NULL).  *frames_total (host,
+ * may be NULL) receives the number of emulated frames after the stream is synchronised. */
+int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, const float *hof_genomes,
+                 const double *hof_fitness, int32_t n_hof, const int32_t *hof_pick, uint64_t seed,
+                 uint64_t generation, double *fitness, double *rewards, int32_t *frames,
+                 uint64_t *frames_total, void *stream);
+/* Same through HOST buffers: copies genomes (and HoF) in and fitness out, synchronises. */
+int ngp_evaluate_host(ngp_handle *h, const float *genomes, int32_t n, const float *hof_genomes,
+                      const double *hof_fitness, int32_t n_hof, uint64_t seed, uint64_t generation,
+                      double *fitness, uint64_t *frames_total);
+
+/* ---- K4: GA step.  Replaces toolbox.select / varAnd(mate, mutate) inside eaSimple
+ * (ga.py:89-94, main.py:165-170; DEAP selTournament, cxBlend, mutGaussian).
+ * Injected noise (all device, all optional = NULL -> Philox(seed, generation)). */
+typedef struct {
+    const int32_t *sel_draws;     /* [n][tournament_size] aspirant indices */
+    const uint8_t *cx_do;         /* [n/2] */
+    const float *cx_u;            /* [n/2][G] uniforms in [0,1) */
+    const uint8_t *mut_do;        /* [n] */
+    const float *mut_u;           /* [n][G] uniforms */
+    const float *mut_z;           /* [n][G] standard normals */
+} ngp_noise;
+/* genomes f32[n][G], fitness f64[n] -> next f32[n][G], parent_idx i32[n] (selection winners),
+ * invalid u8[n] (1 = needs re-evaluation), stats f64[4] = avg std min max of fitness (main.py:158-162). */
+int ngp_ga_step(ngp_handle *h, const float *genomes, const double *fitness, int32_t n, uint64_t seed,
+                uint64_t generation, const ngp_noise *noise, float *next, int32_t *parent_idx,
+                uint8_t *invalid, double *stats, void *stream);
+/* population init: each gene uniform [0,1) (ga.py:85-87) from Philox(seed) */
+int ngp_init_population(ngp_handle *h, float *genomes, int32_t n, uint64_t seed, void *stream);
+
+/* Device-side timing of the dominant kernel (the fused rollout) with CUDA events recorded on the
+ * launching stream around each launch.  ngp_profile_read synchronises the recorded events, returns
+ * the accumulated milliseconds and launch count since the previous read, and resets both. */
+int ngp_profile_enable(ngp_handle *h, int32_t on);
+int ngp_profile_read(ngp_handle *h, double *rollout_ms, int32_t *rollout_launches);
+
+/* kernels launched by this handle so far (bench.py's gpu_launches) */
+uint64_t ngp_launch_count(const ngp_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,467 @@
+// ngp_ops.cu -- stand-alone operator kernels of libngp.so:
+//   K2  frame -> observation          utils.find_stuff / get_rect_quickly  (utils.py:14-19, 60-68)
+//   K3  per-genome grouped MLP        numpy_nn.NeuralNetwork.run           (numpy_nn.py:120-137)
+//   K4  GA step                       DEAP selTournament / cxBlend / mutGaussian / varAnd as wired in
+//                                     ga.py:85-94 and driven by eaSimple at main.py:165-170
+#include <math.h>
+
+#include "ngp_internal.h"
+
+// =================================================================================================
+// K2: find_stuff.  HBM-bound: 76 800 B of cropped RGB per frame, read once with 16-byte loads.
+// The crop [34,194) x 160 x 3 is one contiguous byte range of the frame; a 16-byte vector never
+// straddles a row (480 = 30 * 16), and its channel phase is (vector index mod 3).
+// =================================================================================================
+struct FindStuffPatterns { uint32_t w[3][3][4]; };   // [phase][target][word]: target bytes repeated with the phase
+
+__global__ void __launch_bounds__(256) find_stuff_kernel(const uint8_t *__restrict__ frames, int n, FindStuffPatterns pat,
+                                                         float *__restrict__ loc, uint8_t *__restrict__ valid)
+{
+    constexpr int VEC_PER_FRAME = (a26::CROP_BOTTOM - a26::CROP_TOP) * 480 / 16;   // 4800
+    __shared__ uint32_t red[8][9];
+    for (int f = blockIdx.x; f < n; f += gridDim.x) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(frames + (size_t)f * (a26::FB_ROWS * 480) + a26::CROP_TOP * 480);
+        uint32_t acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};       // per target: count, sum row, sum col
+        for (int k = threadIdx.x; k < VEC_PER_FRAME; k += 256) {
+            const uint4 v = __ldg(&src[k]);
+            const uint32_t words[4] = {v.x, v.y, v.z, v.w};
+            const int phase = k % 3, row = k / 30, byte0 = (k % 30) * 16;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    uint32_t m = __vcmpeq4(words[wi], pat.w[phase][t][wi]) & 0x01010101u;
+                    if (m) {
+                        const int b = byte0 + wi * 4;
+                        uint32_t c = __popc(m);
+                        uint32_t sc = (m & 1) * (b / 3) + ((m >> 8) & 1) * ((b + 1) / 3) + ((m >> 16) & 1) * ((b + 2) / 3) +
+                                      ((m >> 24) & 1) * ((b + 3) / 3);
+                        acc[3 * t] += c; acc[3 * t + 1] += c * row; acc[3 * t + 2] += sc;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            for (int off = 16; off; off >>= 1) acc[i] += __shfl_down_sync(0xFFFFFFFFu, acc[i], off);
+        if ((threadIdx.x & 31) == 0)
+            for (int i = 0; i < 9; ++i) red[threadIdx.x >> 5][i] = acc[i];
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            const int t = threadIdx.x;
+            uint32_t c = 0, sr = 0, sc = 0;
+            for (int w = 0; w < 8; ++w) { c += red[w][3 * t]; sr += red[w][3 * t + 1]; sc += red[w][3 * t + 2]; }
+            valid[f * 3 + t] = c > 0;
+            loc[(f * 3 + t) * 2 + 0] = c ? (float)((double)sr / (double)c) : 0.f;
+            loc[(f * 3 + t) * 2 + 1] = c ? (float)((double)sc / (double)c) : 0.f;
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int ngp_find_stuff(ngp_handle *h, const uint8_t *frames, int32_t n, float *loc, uint8_t *valid, void *stream)
+{
+    NGP_REQUIRE(h && frames && loc && valid && n > 0, "ngp_find_stuff: bad arguments");
+    NGP_REQUIRE(((uintptr_t)frames & 15) == 0, "ngp_find_stuff: frames must be 16-byte aligned");
+    NGP_CUDA(cudaSetDevice(h->device));
+    FindStuffPatterns pat;
+    const uint8_t *targets[3] = {h->cfg.ball_colour, h->cfg.left_colour, h->cfg.right_colour};
+    for (int phase = 0; phase < 3; ++phase)
+        for (int t = 0; t < 3; ++t)
+            for (int w = 0; w < 4; ++w) {
+                uint32_t v = 0;
+                for (int j = 0; j < 4; ++j) v |= (uint32_t)targets[t][(phase + w * 4 + j) % 3] << (8 * j);
+                pat.w[phase][t][w] = v;
+            }
+    int grid = n < h->sm_count * 8 ? n : h->sm_count * 8;
+    find_stuff_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, n, pat, loc, valid);
+    h->launches++;
+    NGP_CUDA(cudaGetLastError());
+    return NGP_OK;
+}
+
+// =================================================================================================
+// K3: grouped MLP forward, FP32 FFMA.
+//   small nets (every layer <= 32 wide): one thread per (genome, env); the genome's weights are read
+//   through the read-only path and broadcast inside the warp.
+//   larger nets: one launch per layer, a CTA computes a 64(env) x 64(out) tile for one genome from
+//   K-chunks of activations and weights staged in shared memory (4x4 register tile per thread).
+// The last layer's pre-activations are accumulated in FP64 and the action is decided on the FP64
+// sigmoids so the reference's argmax (first maximum wins; both outputs saturating to 1.0 -> index 0)
+// is reproduced (SURVEY hard part 4).
+// =================================================================================================
+__device__ __forceinline__ float sigmoid_f32(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+__global__ void __launch_bounds__(128) mlp_small_kernel(const float *__restrict__ genomes, const float *__restrict__ x, int n_genomes, int envs,
+                                                        pol::Shape sh, int G, uint8_t *__restrict__ act, float *__restrict__ out)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_genomes * envs) return;
+    const int g = (int)(idx / envs);
+    const float *w = genomes + (size_t)g * G;
+    const int bias = sh.bias ? 1 : 0;
+    float cur[pol::FUSED_MAX_WIDTH + 1], nxt[pol::FUSED_MAX_WIDTH + 1];
+    const int n_in = sh.nodes[0];
+    for (int i = 0; i < n_in; ++i) cur[i] = x[idx * n_in + i];
+    const int L = sh.n_layers - 1;
+    double zlast[pol::FUSED_MAX_WIDTH];
+    for (int l = 0; l < L; ++l) {
+        const int ni = sh.nodes[l], no = sh.nodes[l + 1];
+        if (bias) cur[ni] = 1.0f;
+        for (int o = 0; o < no; ++o) {
+            if (l == L - 1) {
+                double z = 0.0;
+                for (int i = 0; i < ni + bias; ++i) z += (double)__ldg(&w[o * (ni + bias) + i]) * (double)cur[i];
+                zlast[o] = z;
+                nxt[o] = (float)pol::det_sigmoid(z);
+            } else {
+                float z = 0.f;
+                for (int i = 0; i < ni + bias; ++i) z = fmaf(__ldg(&w[o * (ni + bias) + i]), cur[i], z);
+                nxt[o] = sigmoid_f32(z);
+            }
+        }
+        w += (ni + bias) * no;
+        for (int o = 0; o < no; ++o) cur[o] = nxt[o];
+    }
+    const int n_out = sh.nodes[L];
+    int best = 0;
+    double sbest = pol::det_sigmoid(zlast[0]);
+    for (int o = 1; o < n_out; ++o) {
+        double s = pol::det_sigmoid(zlast[o]);
+        if (s > sbest) { sbest = s; best = o; }
+    }
+    act[idx] = best == 0 ? pol::ACT_UP : pol::ACT_DOWN;
+    if (out) for (int o = 0; o < n_out; ++o) out[idx * n_out + o] = cur[o];
+}
+
+// one layer: in[g][e][ni] (+ implicit bias 1) x W_g[no][ni+bias] -> out[g][e][no] (sigmoid), or for the
+// last layer FP64 pre-activations zout[g][e][no]
+template <bool LAST>
+__global__ void __launch_bounds__(256) mlp_layer_kernel(const float *__restrict__ genomes, size_t w_off, int G, const float *__restrict__ in,
+                                                        int envs, int ni, int no, int bias, float *__restrict__ outp, double *__restrict__ zout)
+{
+    constexpr int TE = 64, TO = 64, TK = 32;
+    __shared__ float As[TK][TE + 1];     // activations, k-major
+    __shared__ float Ws[TK][TO + 1];     // weights, k-major
+    const int g = blockIdx.z, e0 = blockIdx.y * TE, o0 = blockIdx.x * TO;
+    const float *W = genomes + (size_t)g * G + w_off;
+    const float *A = in + (size_t)g * envs * ni;
+    const int K = ni + bias;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // 16 x 16 threads, 4x4 outputs each
+    float acc[4][4];
+    double dacc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; dacc[i][j] = 0.0; }
+    for (int k0 = 0; k0 < K; k0 += TK) {
+        for (int i = threadIdx.x; i < TK * TE; i += 256) {
+            const int e = i / TK, k = i % TK;
+            float v = 0.f;
+            if (e0 + e < envs && k0 + k < K) v = (k0 + k < ni) ? A[(size_t)(e0 + e) * ni + k0 + k] : 1.0f;
+            As[k][e] = v;
+        }
+        for (int i = threadIdx.x; i < TK * TO; i += 256) {
+            const int o = i / TK, k = i % TK;
+            Ws[k][o] = (o0 + o < no && k0 + k < K) ? __ldg(&W[(size_t)(o0 + o) * K + k0 + k]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < TK; ++k) {
+            float a[4], w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; w[i] = Ws[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (LAST) dacc[i][j] += (double)a[i] * (double)w[j];
+                    else acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = e0 + ty * 4 + i, o = o0 + tx * 4 + j;
+            if (e < envs && o < no) {
+                if (LAST) zout[((size_t)g * envs + e) * no + o] = dacc[i][j];
+                else outp[((size_t)g * envs + e) * no + o] = sigmoid_f32(acc[i][j]);
+            }
+        }
+}
+
+__global__ void mlp_decide_kernel(const double *__restrict__ z, long long rows, int n_out, uint8_t *__restrict__ act, float *__restrict__ out)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    int best = 0;
+    double sbest = 0.0;
+    for (int o = 0; o < n_out; ++o) {
+        double s = pol::det_sigmoid(z[r * n_out + o]);
+        if (out) out[r * n_out + o] = (float)s;
+        if (o == 0 || s > sbest) { sbest = s; best = o; }
+    }
+    act[r] = best == 0 ? pol::ACT_UP : pol::ACT_DOWN;
+}
+
+struct MlpScratch { float *a, *b; double *z; size_t cap_ab, cap_z; };
+static MlpScratch g_mlp_scratch[64];   // per device
+
+extern "C" int ngp_mlp_forward(ngp_handle *h, const float *genomes, const float *x, int32_t n_genomes, int32_t envs, uint8_t *act,
+                               float *out, void *stream)
+{
+    NGP_REQUIRE(h && genomes && x && act && n_genomes > 0 && envs > 0, "ngp_mlp_forward: bad arguments");
+    NGP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const pol::Shape &sh = h->shape;
+    int widest = 0;
+    for (int i = 0; i < sh.n_layers; ++i) widest = sh.nodes[i] > widest ? sh.nodes[i] : widest;
+    const long long rows = (long long)n_genomes * envs;
+    if (widest <= pol::FUSED_MAX_WIDTH) {
+        mlp_small_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(genomes, x, n_genomes, envs, sh, h->gene_size, act, out);
+        h->launches++;
+        NGP_CUDA(cudaGetLastError());
+        return NGP_OK;
+    }
+    MlpScratch &sc = g_mlp_scratch[h->device];
+    const size_t need_ab = (size_t)rows * widest, need_z = (size_t)rows * sh.nodes[sh.n_layers - 1];
+    if (need_ab > sc.cap_ab) {
+        cudaFree(sc.a); cudaFree(sc.b); sc.cap_ab = 0;
+        NGP_CUDA(cudaMalloc(&sc.a, need_ab * sizeof(float)));
+        NGP_CUDA(cudaMalloc(&sc.b, need_ab * sizeof(float)));
+        sc.cap_ab = need_ab;
+    }
+    if (need_z > sc.cap_z) {
+        cudaFree(sc.z); sc.cap_z = 0;
+        NGP_CUDA(cudaMalloc(&sc.z, need_z * sizeof(double)));
+        sc.cap_z = need_z;
+    }
+    const float *in = x;
+    float *bufs[2] = {sc.a, sc.b};
+    size_t w_off = 0;
+    const int bias = sh.bias ? 1 : 0, L = sh.n_layers - 1;
+    for (int l = 0; l < L; ++l) {
+        const int ni = sh.nodes[l], no = sh.nodes[l + 1];
+        dim3 grid((no + 63) / 64, (envs + 63) / 64, n_genomes);
+        if (l == L - 1) mlp_layer_kernel<true><<<grid, 256, 0, st>>>(genomes, w_off, h->gene_size, in, envs, ni, no, bias, nullptr, sc.z);
+        else mlp_layer_kernel<false><<<grid, 256, 0, st>>>(genomes, w_off, h->gene_size, in, envs, ni, no, bias, bufs[l & 1], nullptr);
+        h->launches++;
+        NGP_CUDA(cudaGetLastError());
+        in = bufs[l & 1];
+        w_off += (size_t)(ni + bias) * no;
+    }
+    mlp_decide_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(sc.z, rows, sh.nodes[L], act, out);
+    h->launches++;
+    NGP_CUDA(cudaGetLastError());
+    return NGP_OK;
+}
+
+// =================================================================================================
+// K4: GA step.  Counter-based RNG: Philox4x32-10 keyed by the seed; the counter encodes
+// (slot, block-within-slot, generation, stream) so results do not depend on launch geometry.
+// =================================================================================================
+enum : uint32_t { STREAM_SELECT = 0x53454C31u, STREAM_CXDO = 0x43584431u, STREAM_CXU = 0x43585531u, STREAM_MUTDO = 0x4D544431u,
+                  STREAM_MUTU = 0x4D545531u, STREAM_MUTZ = 0x4D545A31u, STREAM_INIT = 0x494E4931u };
+
+__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }   // [0,1)
+
+__global__ void init_population_kernel(float *__restrict__ genomes, long long total, uint64_t seed)
+{
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one Philox call -> 4 genes
+    if (q * 4 >= total) return;
+    uint32_t o[4];
+    pol::philox4x32((uint32_t)q, (uint32_t)(q >> 32), 0, STREAM_INIT, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    for (int j = 0; j < 4; ++j)
+        if (q * 4 + j < total) genomes[q * 4 + j] = u01(o[j]);
+}
+
+// avg / std (population, ddof=0) / min / max of the fitness vector (main.py:158-162)
+__global__ void __launch_bounds__(1024) fitness_stats_kernel(const double *__restrict__ fitness, int n, double *__restrict__ stats)
+{
+    __shared__ double s_sum[32], s_min[32], s_max[32];
+    __shared__ double s_mean;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double sum = 0.0, mn = INFINITY, mx = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { double f = fitness[i]; sum += f; mn = fmin(mn, f); mx = fmax(mx, f); }
+    for (int off = 16; off; off >>= 1) {
+        sum += __shfl_down_sync(0xFFFFFFFFu, sum, off);
+        mn = fmin(mn, __shfl_down_sync(0xFFFFFFFFu, mn, off));
+        mx = fmax(mx, __shfl_down_sync(0xFFFFFFFFu, mx, off));
+    }
+    if (lane == 0) { s_sum[warp] = sum; s_min[warp] = mn; s_max[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0, a = INFINITY, b = -INFINITY;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t += s_sum[w]; a = fmin(a, s_min[w]); b = fmax(b, s_max[w]); }
+        s_mean = t / n; stats[0] = s_mean; stats[2] = a; stats[3] = b;
+    }
+    __syncthreads();
+    const double mean = s_mean;
+    double sq = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { double d = fitness[i] - mean; sq += d * d; }
+    for (int off = 16; off; off >>= 1) sq += __shfl_down_sync(0xFFFFFFFFu, sq, off);
+    __syncthreads();
+    if (lane == 0) s_sum[warp] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_sum[w];
+        stats[1] = sqrt(t / n);
+    }
+}
+
+// selTournament: one warp per offspring slot; lanes split the T draws; winner = max fitness, first in
+// draw order on ties.
+__global__ void __launch_bounds__(256) select_tournament_kernel(const double *__restrict__ fitness, int n, int T, const int32_t *__restrict__ draws,
+                                                                uint64_t seed, uint64_t generation, int32_t *__restrict__ parent_idx)
+{
+    const int slot = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (slot >= n) return;
+    double best_f = -INFINITY;
+    int best_pos = 0x7FFFFFFF, best_idx = -1;
+    if (draws) {
+        for (int j = lane; j < T; j += 32) {
+            const int idx = draws[(size_t)slot * T + j];
+            const double f = fitness[idx];
+            if (best_idx < 0 || f > best_f) { best_f = f; best_pos = j; best_idx = idx; }
+        }
+    } else {
+        // draw j comes from Philox block j/4, word j%4; lanes take whole blocks
+        for (int b = lane; b * 4 < T; b += 32) {
+            uint32_t o[4];
+            pol::philox4x32((uint32_t)slot, (uint32_t)b, (uint32_t)generation, STREAM_SELECT, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+            for (int w = 0; w < 4 && b * 4 + w < T; ++w) {
+                const int idx = (int)(((uint64_t)o[w] * (uint64_t)n) >> 32);
+                const double f = fitness[idx];
+                if (best_idx < 0 || f > best_f) { best_f = f; best_pos = b * 4 + w; best_idx = idx; }
+            }
+        }
+    }
+    for (int off = 16; off; off >>= 1) {
+        const double of = __shfl_down_sync(0xFFFFFFFFu, best_f, off);
+        const int op = __shfl_down_sync(0xFFFFFFFFu, best_pos, off);
+        const int oi = __shfl_down_sync(0xFFFFFFFFu, best_idx, off);
+        if (oi >= 0 && (best_idx < 0 || of > best_f || (of == best_f && op < best_pos))) { best_f = of; best_pos = op; best_idx = oi; }
+    }
+    if (lane == 0) parent_idx[slot] = best_idx;
+}
+
+// varAnd: clone selected parents, blend-crossover pairs (0,1),(2,3).., then Gaussian mutation.
+// One thread per (pair, gene).  Every FP32 operation is individually rounded (no FMA contraction) so
+// that, given injected noise, the children match the numpy restatement bit-for-bit.
+__global__ void __launch_bounds__(256) vary_kernel(const float *__restrict__ genomes, const int32_t *__restrict__ parent_idx, int n, int G,
+                                                   ngp_noise noise, uint64_t seed, uint64_t generation, float cxpb, float alpha, float mutpb,
+                                                   float mu, float sigma, float indpb, float *__restrict__ next, uint8_t *__restrict__ invalid)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pairs = (n + 1) / 2;
+    if (tid >= (long long)pairs * G) return;
+    const int pair = (int)(tid / G), gene = (int)(tid % G);
+    const int i0 = 2 * pair, i1 = 2 * pair + 1;
+    const bool has1 = i1 < n;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), gen = (uint32_t)generation;
+    float x0 = genomes[(size_t)parent_idx[i0] * G + gene];
+    float x1 = has1 ? genomes[(size_t)parent_idx[i1] * G + gene] : 0.f;
+    uint32_t o[4];
+    // ---- mate (ga.py:89, cxBlend) ----
+    bool do_cx = false;
+    if (has1) {
+        if (noise.cx_do) do_cx = noise.cx_do[pair] != 0;
+        else { pol::philox4x32((uint32_t)pair, 0, gen, STREAM_CXDO, k0, k1, o); do_cx = u01(o[0]) < cxpb; }
+    }
+    if (do_cx) {
+        float u;
+        if (noise.cx_u) u = noise.cx_u[(size_t)pair * G + gene];
+        else { pol::philox4x32((uint32_t)pair, (uint32_t)(gene >> 2), gen, STREAM_CXU, k0, k1, o); u = u01(o[gene & 3]); }
+        const float gamma = __fsub_rn(__fmul_rn((float)(1.0 + 2.0 * (double)alpha), u), alpha);
+        const float one_m = __fsub_rn(1.0f, gamma);
+        const float c0 = __fadd_rn(__fmul_rn(one_m, x0), __fmul_rn(gamma, x1));
+        const float c1 = __fadd_rn(__fmul_rn(gamma, x0), __fmul_rn(one_m, x1));
+        x0 = c0; x1 = c1;
+    }
+    // ---- mutate (ga.py:91-92, mutGaussian) ----
+    bool do_mut[2];
+    for (int s = 0; s < 2; ++s) {
+        const int ind = s ? i1 : i0;
+        if (s && !has1) { do_mut[s] = false; continue; }
+        if (noise.mut_do) do_mut[s] = noise.mut_do[ind] != 0;
+        else { pol::philox4x32((uint32_t)ind, 0, gen, STREAM_MUTDO, k0, k1, o); do_mut[s] = u01(o[0]) < mutpb; }
+        if (do_mut[s]) {
+            float u, z;
+            if (noise.mut_u) u = noise.mut_u[(size_t)ind * G + gene];
+            else { pol::philox4x32((uint32_t)ind, (uint32_t)(gene >> 2), gen, STREAM_MUTU, k0, k1, o); u = u01(o[gene & 3]); }
+            if (noise.mut_z) z = noise.mut_z[(size_t)ind * G + gene];
+            else {      // Box-Muller on two words of a per-gene Philox block
+                pol::philox4x32((uint32_t)ind, (uint32_t)gene, gen, STREAM_MUTZ, k0, k1, o);
+                const float u1 = ((float)(o[0] >> 8) + 1.0f) * (1.0f / 16777216.0f);      // (0,1]
+                const float u2 = u01(o[1]);
+                z = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+            }
+            if (u < indpb) {
+                const float step = __fadd_rn(mu, __fmul_rn(sigma, z));
+                if (s) x1 = __fadd_rn(x1, step); else x0 = __fadd_rn(x0, step);
+            }
+        }
+    }
+    next[(size_t)i0 * G + gene] = x0;
+    if (has1) next[(size_t)i1 * G + gene] = x1;
+    if (gene == 0) {
+        invalid[i0] = (do_cx || do_mut[0]) ? 1 : 0;
+        if (has1) invalid[i1] = (do_cx || do_mut[1]) ? 1 : 0;
+    }
+}
+
+static int32_t *g_parent_scratch[64];
+static size_t g_parent_cap[64];
+
+extern "C" int ngp_ga_step(ngp_handle *h, const float *genomes, const double *fitness, int32_t n, uint64_t seed, uint64_t generation,
+                           const ngp_noise *noise, float *next, int32_t *parent_idx, uint8_t *invalid, double *stats, void *stream)
+{
+    NGP_REQUIRE(h && genomes && fitness && next && invalid && n > 0, "ngp_ga_step: bad arguments");
+    NGP_REQUIRE(genomes != next, "ngp_ga_step: next must not alias genomes");
+    NGP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ngp_noise nz;
+    memset(&nz, 0, sizeof(nz));
+    if (noise) nz = *noise;
+    int T = h->cfg.tournament_size;
+    if (T < 1) T = 1;
+    if (!parent_idx) {
+        if ((size_t)n > g_parent_cap[h->device]) {
+            cudaFree(g_parent_scratch[h->device]); g_parent_cap[h->device] = 0;
+            NGP_CUDA(cudaMalloc(&g_parent_scratch[h->device], (size_t)n * sizeof(int32_t)));
+            g_parent_cap[h->device] = n;
+        }
+        parent_idx = g_parent_scratch[h->device];
+    }
+    if (stats) {
+        fitness_stats_kernel<<<1, 1024, 0, st>>>(fitness, n, stats);
+        h->launches++;
+        NGP_CUDA(cudaGetLastError());
+    }
+    select_tournament_kernel<<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(fitness, n, T, nz.sel_draws, seed, generation, parent_idx);
+    h->launches++;
+    NGP_CUDA(cudaGetLastError());
+    const long long work = (long long)((n + 1) / 2) * h->gene_size;
+    vary_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(genomes, parent_idx, n, h->gene_size, nz, seed, generation, h->cfg.cxpb,
+                                                               h->cfg.cx_alpha, h->cfg.mutpb, h->cfg.mut_mu, h->cfg.mut_sigma,
+                                                               h->cfg.mut_indpb, next, invalid);
+    h->launches++;
+    NGP_CUDA(cudaGetLastError());
+    return NGP_OK;
+}
+
+extern "C" int ngp_init_population(ngp_handle *h, float *genomes, int32_t n, uint64_t seed, void *stream)
+{
+    NGP_REQUIRE(h && genomes && n > 0, "ngp_init_population: bad arguments");
+    NGP_CUDA(cudaSetDevice(h->device));
+    const long long total = (long long)n * h->gene_size, calls = (total + 3) / 4;
+    init_population_kernel<<<(unsigned)((calls + 255) / 256), 256, 0, (cudaStream_t)stream>>>(genomes, total, seed);
+    h->launches++;
+    NGP_CUDA(cudaGetLastError());
+    return NGP_OK;
+}

@@ -1,0 +1,170 @@
+// host_sim.cpp -- TEST INFRASTRUCTURE.  Compiles the device-side source of the CUDA core
+// (csrc/a26_core.cuh, policy.cuh, rollout.cuh) for the CPU behind a small intrinsics shim, so the
+// kernel logic can be debugged against the oracle in the build container, which has no GPU.  It is
+// not part of the product library, is never loaded by the package, and proves nothing about the
+// GPU build: the `-m gpu` parity tests do that through libngp.so.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#define __CUDACC__ 1
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__
+static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline uint32_t __brev(uint32_t v)
+{
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+    return __builtin_bswap32(v);
+}
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+    sh &= 31;
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+}
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+
+#include "../../neuro_genetic_pong_self_play_b200/csrc/rollout.cuh"
+#include "../../neuro_genetic_pong_self_play_b200/csrc/host_tables.h"
+
+namespace {
+// same palette the product uploads (csrc/ngp_core.cu: ngp_ntsc_palette)
+const uint32_t kPalette[128] = {
+    0x000000, 0x4a4a4a, 0x6f6f6f, 0x8e8e8e, 0xaaaaaa, 0xc0c0c0, 0xd6d6d6, 0xececec, 0x484800, 0x69690f, 0x86861d, 0xa2a22a,
+    0xbbbb35, 0xd2d240, 0xe8e84a, 0xfcfc54, 0x7c2c00, 0x904811, 0xa26221, 0xb47a30, 0xc3903d, 0xd2a44a, 0xdfb755, 0xecc860,
+    0x901c00, 0xa33915, 0xb55328, 0xc66c3a, 0xd5824a, 0xe39759, 0xf0aa67, 0xfcbc74, 0x940000, 0xa71a1a, 0xb83232, 0xc84848,
+    0xd65c5c, 0xe46f6f, 0xf08080, 0xfc9090, 0x840064, 0x97197a, 0xa8308f, 0xb846a2, 0xc659b3, 0xd46cc3, 0xe07cd2, 0xec8ce0,
+    0x500084, 0x68199a, 0x7d30ad, 0x9246c0, 0xa459d0, 0xb56ce0, 0xc57cee, 0xd48cfc, 0x140090, 0x331aa3, 0x4e32b5, 0x6848c6,
+    0x7f5cd5, 0x956fe3, 0xa980f0, 0xbc90fc, 0x000094, 0x181aa7, 0x2d32b8, 0x4248c8, 0x545cd6, 0x656fe4, 0x7580f0, 0x8490fc,
+    0x001c88, 0x183b9d, 0x2d57b0, 0x4272c2, 0x548ad2, 0x65a0e1, 0x75b5ef, 0x84c8fc, 0x003064, 0x185080, 0x2d6d98, 0x4288b0,
+    0x54a0c5, 0x65b7d9, 0x75cceb, 0x84e0fc, 0x004030, 0x18624e, 0x2d8169, 0x429e82, 0x54b899, 0x65d1ae, 0x75e7c2, 0x84fcd4,
+    0x004400, 0x1a661a, 0x328432, 0x48a048, 0x5cba5c, 0x6fd26f, 0x80e880, 0x90fc90, 0x143c00, 0x355f18, 0x527e2d, 0x6e9c42,
+    0x87b754, 0x9ed065, 0xb4e775, 0xc8fc84, 0x303800, 0x505916, 0x6d762b, 0x88923e, 0xa0ab4f, 0xb7c25f, 0xccd86e, 0xe0ec7c,
+    0x482c00, 0x694d14, 0x866a26, 0xa28638, 0xbb9f47, 0xd2b656, 0xe8cc63, 0xfce070,
+};
+
+struct Sim {
+    a26::Tables T;
+    std::vector<uint32_t> needed;
+    a26::Snapshot start[2];
+    // one stepwise env
+    a26::Chip s;
+    a26::CpuRegs r;
+    uint32_t ram_words[32 * 32];   // lane 0 of a warp-interleaved block
+};
+}  // namespace
+
+extern "C" {
+
+void *hs_create(const uint8_t *rom)
+{
+    Sim *sim = new Sim();
+    const uint8_t ball[3] = {236, 236, 236}, left[3] = {213, 130, 74}, right[3] = {92, 186, 92};
+    ngp_host::build_tables(sim->T, rom, ball, left, right, kPalette);
+    sim->needed.resize(a26::TRIGMAX + 1);
+    ngp_host::build_paddle_table(sim->needed.data());
+    a26::Ram ram{sim->ram_words};
+    for (int st = 0; st < 2; ++st) {
+        roll::build_start_state(st, sim->s, sim->r, sim->T, ram, sim->needed.data());
+        roll::store_snapshot(&sim->start[st], sim->s, sim->r, ram);
+    }
+    return sim;
+}
+void hs_destroy(void *h) { delete (Sim *)h; }
+
+void hs_env_reset(void *h, int state)
+{
+    Sim *sim = (Sim *)h;
+    roll::load_snapshot(&sim->start[state], sim->s, sim->r, a26::Ram{sim->ram_words});
+}
+void hs_env_power_on(void *h)
+{
+    Sim *sim = (Sim *)h;
+    a26::power_on(sim->s, sim->r, sim->T, a26::Ram{sim->ram_words}, sim->needed.data());
+}
+
+// raw console input step (like a26o_run_frame)
+int hs_env_run_frame(void *h, int swchb, int fire, int dec, int inc, uint8_t *ram_out, uint8_t *fb, double *loc, uint8_t *valid,
+                     uint8_t *regs, uint32_t *digest)
+{
+    Sim *sim = (Sim *)h;
+    a26::Ram ram{sim->ram_words};
+    a26::Chip &s = sim->s;
+    a26::apply_input(s, sim->needed.data(), (uint32_t)swchb, (uint32_t)fire, (uint32_t)dec, (uint32_t)inc);
+    a26::clear_obs(s);
+    if (fb) memset(fb, 0, 210 * 160);
+    a26::run_frame<true>(s, sim->r, sim->T, ram, fb);
+    if (ram_out) for (int i = 0; i < 128; ++i) ram_out[i] = (uint8_t)ram.rd(i);
+    if (loc && valid)
+        for (int t = 0; t < 3; ++t) {
+            valid[t] = s.cnt[t] > 0;
+            loc[2 * t] = s.cnt[t] ? (double)s.sy[t] / (double)s.cnt[t] : 0.0;
+            loc[2 * t + 1] = s.cnt[t] ? (double)s.sx[t] / (double)s.cnt[t] : 0.0;
+        }
+    if (regs) {
+        const a26::CpuRegs &r = sim->r;
+        regs[0] = (uint8_t)r.a; regs[1] = (uint8_t)r.x; regs[2] = (uint8_t)r.y; regs[3] = (uint8_t)r.sp; regs[4] = (uint8_t)a26::pack_p(r);
+        regs[5] = (uint8_t)r.pc; regs[6] = (uint8_t)(r.pc >> 8); regs[7] = s.error;
+    }
+    if (digest) {
+        digest[0] = s.cx;
+        digest[1] = (uint32_t)s.posp0 | ((uint32_t)s.posp1 << 8) | ((uint32_t)s.posm0 << 16) | ((uint32_t)s.posm1 << 24);
+        digest[2] = (uint32_t)s.posbl | ((uint32_t)s.vblank << 8) | ((uint32_t)s.ctrlpf << 16) | ((uint32_t)s.vdelbl << 24);
+        digest[3] = (uint32_t)s.charge[0] | ((uint32_t)s.charge[1] << 16);
+        digest[4] = (uint32_t)s.charge[2] | ((uint32_t)s.charge[3] << 16);
+        digest[5] = (uint32_t)s.grp0_new | ((uint32_t)s.grp1_new << 8) | ((uint32_t)s.enabl_new << 16) | ((uint32_t)s.enabl_old << 24);
+        digest[6] = (sim->r.cyc - sim->r.cpu_ls) % a26::LINE_CYCLES;
+        digest[7] = s.dump_enabled;
+    }
+    return s.error;
+}
+
+int hs_env_step(void *h, const uint8_t *action16, uint8_t *ram_out, uint8_t *fb, double *loc, uint8_t *valid, uint8_t *regs, uint32_t *digest)
+{
+    uint32_t fire, dec, inc;
+    roll::action_to_input(action16, fire, dec, inc);
+    return hs_env_run_frame(h, 0x3F, (int)fire, (int)dec, (int)inc, ram_out, fb, loc, valid, regs, digest);
+}
+
+// fused evaluation, lanes executed one after another
+void hs_evaluate(void *h, const int32_t *nodes, int n_layers, int bias, int schedule, int games, int max_frames, const float *genomes, int n,
+                 const float *hof_genomes, const double *hof_fitness, int n_hof, const int32_t *hof_pick, uint64_t seed,
+                 uint64_t generation, double *rewards, int32_t *frames)
+{
+    Sim *sim = (Sim *)h;
+    roll::RolloutParams p;
+    memset(&p, 0, sizeof(p));
+    p.tables = &sim->T; p.needed = sim->needed.data(); p.start = sim->start;
+    p.genomes = genomes; p.hof_genomes = hof_genomes; p.hof_fitness = hof_fitness; p.hof_pick = hof_pick;
+    p.n = n; p.n_hof = n_hof; p.games = games; p.schedule = schedule; p.win_score = 3; p.timeout_thresh = 2000; p.max_frames = max_frames;
+    p.time_scaler = 100.0; p.paddle_height = 16.0; p.seed = seed; p.generation = generation;
+    p.shape.n_layers = n_layers; p.shape.bias = bias;
+    int G = 0;
+    for (int i = 0; i < n_layers; ++i) p.shape.nodes[i] = nodes[i];
+    for (int i = 0; i + 1 < n_layers; ++i) G += (nodes[i] + (bias ? 1 : 0)) * nodes[i + 1];
+    p.G = G;
+    p.rewards = rewards; p.frames = frames;
+    a26::Ram ram{sim->ram_words};
+    for (int e = 0; e < n * games; ++e) {
+        roll::Episode ep;
+        a26::Chip s; a26::CpuRegs r;
+        roll::episode_begin(ep, p, e, s, r, ram);
+        double reward = 0.0;
+        while (!roll::episode_frame(ep, p, s, r, sim->T, ram, &reward)) {}
+        rewards[e] = reward; frames[e] = ep.frame;
+    }
+}
+
+}  // extern "C"
