@@ -1,0 +1,73 @@
+"""CPU-side check of the CUDA core's SOURCE: tests/host_sim compiles csrc/*.cuh for the host behind
+an intrinsics shim and is compared with the oracle.  This is a debugging aid for the GPU-less build
+container; the binding parity evidence is tests/test_gpu_parity.py on a real B200."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "host_sim", "host_sim.cpp")
+LIB = os.path.join(ROOT, "tests", "host_sim", "libhost_sim.so")
+vp = ctypes.c_void_p
+
+
+@pytest.fixture(scope="module")
+def hs():
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", LIB, SRC])
+    L = ctypes.CDLL(LIB)
+    L.hs_create.restype = vp
+    L.hs_env_reset.argtypes = [vp, ctypes.c_int]
+    L.hs_env_power_on.argtypes = [vp]
+    L.hs_env_step.argtypes = [vp] * 8
+    L.hs_evaluate.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, vp,
+                              ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_uint64, vp, vp]
+    return L, vp(L.hs_create(oracle.load_rom()))
+
+
+def P(a):
+    return a.ctypes.data_as(vp)
+
+
+@pytest.mark.parametrize("state,frames,hold", [(None, 120, 3), (0, 500, 4), (1, 700, 7)])
+def test_core_matches_oracle_on_random_traces(hs, state, frames, hold):
+    L, sim = hs
+    rng = np.random.RandomState(frames)
+    env = oracle.Atari()
+    if state is None:
+        env.power_on(); L.hs_env_power_on(sim)
+    else:
+        env.reset_to_state(state); L.hs_env_reset(sim, state)
+    ram = np.zeros(128, np.uint8); fb = np.zeros((210, 160), np.uint8); loc = np.zeros(6); valid = np.zeros(3, np.uint8)
+    regs = np.zeros(8, np.uint8); dig = np.zeros(8, np.uint32)
+    act = np.zeros(16, np.uint8)
+    for f in range(frames):
+        if f % hold == 0:
+            act = np.zeros(16, np.uint8); act[0] = act[15] = 1
+            r, l = rng.randint(0, 3), rng.randint(0, 3)
+            act[4] = r == 1; act[5] = r == 2; act[6] = l == 1; act[7] = l == 2
+        ofb = env.step(act)
+        assert L.hs_env_step(sim, P(act), P(ram), P(fb), P(loc), P(valid), P(regs), P(dig)) == 0
+        assert np.array_equal(env.ram, ram), f
+        assert np.array_equal(env.cpu_regs[:7], regs[:7]), f
+        assert np.array_equal(ofb, fb), f
+        assert np.array_equal(env.tia_digest, dig), f
+        ol, ov = oracle.find_stuff(oracle.fb_to_rgb(ofb))
+        assert np.array_equal(ov, valid) and np.array_equal(ol[ov == 1].ravel(), loc.reshape(3, 2)[valid == 1].ravel()), f
+
+
+def test_fused_rollout_matches_oracle_evaluate(hs):
+    L, sim = hs
+    rng = np.random.RandomState(7)
+    nodes = np.array([6, 2, 2], np.int32)
+    genomes = (rng.random_sample((1, 20)) * 4 - 2).astype(np.float32)
+    hof = (rng.random_sample((3, 20)) * 4 - 2).astype(np.float32); hof_fit = np.array([0.7, 0.3, 0.1])
+    pick = np.array([[2, 0, 1]], np.int32)
+    rew = np.zeros((1, 6)); frm = np.zeros((1, 6), np.int32)
+    L.hs_evaluate(sim, P(nodes), 3, 1, 0, 6, 0, P(genomes), 1, P(hof), P(hof_fit), 3, P(pick), 5, 0, P(rew), P(frm))
+    fit, r, f = oracle.evaluate([6, 2, 2], genomes[0], hof, hof_fit, pick[0], seed=5, genome_id=0)
+    assert np.array_equal(r, rew[0]) and np.array_equal(f, frm[0])
