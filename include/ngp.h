@@ -40,6 +40,9 @@ enum { NGP_ACT_NONE = 0, NGP_ACT_UP = 1, NGP_ACT_DOWN = 2 };
 /* retro save states used by the reference: default ('Start', 1 player vs the cartridge
  * robot, main.py:40) and 'Start.2P' (main.py:21,51) */
 enum { NGP_STATE_START_1P = 0, NGP_STATE_START_2P = 1 };
+/* 6507 core: the cartridge statically translated to CUDA (default, fastest) or the table-driven
+ * interpreter (generic; also the verify-mode core of ngp_env_step) */
+enum { NGP_CORE_TRANSLATED = 1, NGP_CORE_INTERPRETER = 0 };
 /* opponent schedule of one evaluation */
 enum {
     NGP_SCHEDULE_REFERENCE = 0,      /* main.py:33-58: bot, robot, score-bot, 3 x hall of fame */
@@ -65,6 +68,7 @@ typedef struct {
     /* GA rates, config.py:36-43, 49-50 */
     float cxpb, cx_alpha, mutpb, mut_mu, mut_sigma, mut_indpb;
     int32_t tournament_size;                 /* TOURNAMENT_SIZE = POPULATION_SIZE // 4 */
+    int32_t core;                            /* 6507 core of the fused rollout: NGP_CORE_* */
 } ngp_config;
 
 typedef struct ngp_handle ngp_handle;
@@ -89,6 +93,9 @@ int ngp_env_reset(ngp_handle *h, int32_t n_envs, int32_t state_id, void *stream)
  * regs u8[n][8] = A X Y SP P PCL PCH err. */
 int ngp_env_step(ngp_handle *h, const uint8_t *actions, uint8_t *ram, uint8_t *frames,
                  float *loc, uint8_t *valid, uint8_t *regs, void *stream);
+/* same, choosing the 6507 core explicitly (parity tests run both) */
+int ngp_env_step_core(ngp_handle *h, int32_t core, const uint8_t *actions, uint8_t *ram, uint8_t *frames,
+                      float *loc, uint8_t *valid, uint8_t *regs, void *stream);
 /* debug/parity: TIA digest u32[n][8] (collision latches, object positions, paddle charges) */
 int ngp_env_digest(ngp_handle *h, uint32_t *digest, void *stream);
 

@@ -11,10 +11,11 @@ NGP_MAX_LAYERS = 8
 ACT_NONE, ACT_UP, ACT_DOWN = 0, 1, 2
 STATE_START_1P, STATE_START_2P = 0, 1
 SCHEDULE_REFERENCE, SCHEDULE_ROUND_ROBIN = 0, 1
+CORE_INTERPRETER, CORE_TRANSLATED = 0, 1
 
 EXPORTS = [
     "ngp_default_config", "ngp_last_error", "ngp_version", "ngp_create", "ngp_destroy", "ngp_gene_size",
-    "ngp_env_reset", "ngp_env_step", "ngp_env_digest", "ngp_find_stuff", "ngp_mlp_forward", "ngp_evaluate",
+    "ngp_env_reset", "ngp_env_step", "ngp_env_step_core", "ngp_env_digest", "ngp_find_stuff", "ngp_mlp_forward", "ngp_evaluate",
     "ngp_evaluate_host", "ngp_ga_step", "ngp_init_population", "ngp_launch_count", "ngp_profile_enable", "ngp_profile_read",
 ]
 
@@ -27,7 +28,7 @@ class NgpConfig(ctypes.Structure):
         ("scaled_paddle_height", ctypes.c_float), ("ball_colour", ctypes.c_uint8 * 3), ("left_colour", ctypes.c_uint8 * 3),
         ("right_colour", ctypes.c_uint8 * 3), ("pad_", ctypes.c_uint8 * 3),
         ("cxpb", ctypes.c_float), ("cx_alpha", ctypes.c_float), ("mutpb", ctypes.c_float), ("mut_mu", ctypes.c_float),
-        ("mut_sigma", ctypes.c_float), ("mut_indpb", ctypes.c_float), ("tournament_size", ctypes.c_int32),
+        ("mut_sigma", ctypes.c_float), ("mut_indpb", ctypes.c_float), ("tournament_size", ctypes.c_int32), ("core", ctypes.c_int32),
     ]
 
 
@@ -66,6 +67,7 @@ def load(build_if_missing: bool = True):
     L.ngp_gene_size.argtypes = [vp]; L.ngp_gene_size.restype = i32
     L.ngp_env_reset.argtypes = [vp, i32, i32, vp]
     L.ngp_env_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ngp_env_step_core.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.ngp_env_digest.argtypes = [vp, vp, vp]
     L.ngp_find_stuff.argtypes = [vp, vp, i32, vp, vp, vp]
     L.ngp_mlp_forward.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]

@@ -42,6 +42,7 @@ class Config:
     # not in the reference: opponent schedule of one evaluation and a per-episode frame cap
     SCHEDULE: int = _lib.SCHEDULE_REFERENCE
     MAX_FRAMES: int = 0
+    CORE: int = _lib.CORE_TRANSLATED           # 6507 core of the fused rollout
 
     @property
     def GAME_PLAYABLE_HEIGHT(self) -> int:
@@ -93,4 +94,5 @@ class Config:
         c.mut_sigma = self.GAUSSIAN_MUTATION_SIGMA
         c.mut_indpb = self.PROBABILITY_OF_MUTATING_A_SINGLE_GENE
         c.tournament_size = self.TOURNAMENT_SIZE
+        c.core = self.CORE
         return c

@@ -153,6 +153,7 @@ struct Tables {               // per-CTA shared-memory tables
     uint32_t rom[512];        // 2 KiB cartridge as words
     uint32_t decode[256];
     uint8_t weight[128];      // per palette entry: 2 bits per target colour = matching channels
+    uint16_t blockmap[2048];  // ROM offset -> dispatch entry of the statically translated core (0 = none)
 };
 
 #ifdef __CUDACC__
@@ -167,13 +168,14 @@ __device__ __forceinline__ uint32_t rom_byte(const Tables &T, uint32_t addr)
 
 // ---- RAM: word-interleaved shared memory ---------------------------------------------------
 struct Ram {
-    uint32_t *base;   // &warp_ram[lane]
-    __device__ __forceinline__ uint32_t rd(uint32_t a) const { return (base[(a & 0x7C) << 3] >> ((a & 3) << 3)) & 0xFF; }
+    uint32_t *base;   // &warp_ram[lane]; byte b of word w sits at byte offset (w*32)*4 + b from base
+    __device__ __forceinline__ uint32_t rd(uint32_t a) const
+    {
+        return reinterpret_cast<const uint8_t *>(base)[((a & 0x7C) << 5) | (a & 3)];
+    }
     __device__ __forceinline__ void wr(uint32_t a, uint32_t v)
     {
-        uint32_t sh = (a & 3) << 3;
-        uint32_t *p = &base[(a & 0x7C) << 3];
-        *p = (*p & ~(0xFFu << sh)) | ((v & 0xFF) << sh);
+        reinterpret_cast<uint8_t *>(base)[((a & 0x7C) << 5) | (a & 3)] = (uint8_t)v;
     }
 };
 
@@ -295,16 +297,30 @@ __device__ __forceinline__ void accumulate_class(Chip &s, const Tables &T, uint3
 template <bool VERIFY>
 __device__ __noinline__ void render_span(Chip &s, const Tables &T, int x0, int x1, int row, uint8_t *fb_row)
 {
+    const uint32_t grp0 = (s.vdelp0 & 1) ? s.grp0_old : s.grp0_new, grp1 = (s.vdelp1 & 1) ? s.grp1_old : s.grp1_new;
+    const bool bl_on = (((s.vdelbl & 1) ? s.enabl_old : s.enabl_new) & 2) != 0;
+    const bool m0_on = (s.enam0 & 2) && !(s.resmp0 & 2), m1_on = (s.enam1 & 2) && !(s.resmp1 & 2);
+    const bool in_crop_row = row >= CROP_TOP && row < CROP_BOTTOM;
+    if (!(grp0 | grp1) && !bl_on && !m0_on && !m1_on) {
+        // only playfield and background on this span: no collision is possible
+        if (!VERIFY) {
+            if (!in_crop_row) return;
+            uint32_t wts = T.weight[s.colupf >> 1] | T.weight[s.colubk >> 1];
+            if (s.ctrlpf & 2) wts |= T.weight[s.colup0 >> 1] | T.weight[s.colup1 >> 1];
+            if (s.hmove_blank) wts |= T.weight[0];
+            if (!wts) return;                      // none of these colours shares a channel with a target colour
+        }
+    }
     Masks R, PF, BL, P0, P1, M0, M1;
 #pragma unroll
     for (int i = 0; i < 5; ++i) { R.w[i] = range_word(i, x0, x1); PF.w[i] = s.pfmask[i] & R.w[i]; }
     // ball
     BL.w[0] = BL.w[1] = BL.w[2] = BL.w[3] = BL.w[4] = 0;
-    if (((s.vdelbl & 1) ? s.enabl_old : s.enabl_new) & 2) place(BL, (1u << (1u << ((s.ctrlpf >> 4) & 3))) - 1u, s.posbl);
-    player_mask(P0, s.posp0, s.nusiz0, (s.vdelp0 & 1) ? s.grp0_old : s.grp0_new, s.refp0 & 8, s.suppress & 1);
-    player_mask(P1, s.posp1, s.nusiz1, (s.vdelp1 & 1) ? s.grp1_old : s.grp1_new, s.refp1 & 8, s.suppress & 2);
-    if ((s.enam0 & 2) && !(s.resmp0 & 2)) missile_mask(M0, s.posm0, s.nusiz0); else M0.w[0] = M0.w[1] = M0.w[2] = M0.w[3] = M0.w[4] = 0;
-    if ((s.enam1 & 2) && !(s.resmp1 & 2)) missile_mask(M1, s.posm1, s.nusiz1); else M1.w[0] = M1.w[1] = M1.w[2] = M1.w[3] = M1.w[4] = 0;
+    if (bl_on) place(BL, (1u << (1u << ((s.ctrlpf >> 4) & 3))) - 1u, s.posbl);
+    player_mask(P0, s.posp0, s.nusiz0, grp0, s.refp0 & 8, s.suppress & 1);
+    player_mask(P1, s.posp1, s.nusiz1, grp1, s.refp1 & 8, s.suppress & 2);
+    if (m0_on) missile_mask(M0, s.posm0, s.nusiz0); else M0.w[0] = M0.w[1] = M0.w[2] = M0.w[3] = M0.w[4] = 0;
+    if (m1_on) missile_mask(M1, s.posm1, s.nusiz1); else M1.w[0] = M1.w[1] = M1.w[2] = M1.w[3] = M1.w[4] = 0;
 #pragma unroll
     for (int i = 0; i < 5; ++i) { BL.w[i] &= R.w[i]; P0.w[i] &= R.w[i]; P1.w[i] &= R.w[i]; M0.w[i] &= R.w[i]; M1.w[i] &= R.w[i]; }
     bool pf = any_bits(PF), bl = any_bits(BL), p0 = any_bits(P0), p1 = any_bits(P1), m0 = any_bits(M0), m1 = any_bits(M1);
@@ -334,7 +350,7 @@ __device__ __noinline__ void render_span(Chip &s, const Tables &T, int x0, int x
     if (bl && pf && any_and(BL, PF)) cx |= 1u << CX_BLPF;
     s.cx |= (uint16_t)cx;
 
-    const bool in_crop = row >= CROP_TOP && row < CROP_BOTTOM;
+    const bool in_crop = in_crop_row;
     if (!VERIFY && !in_crop) return;
 
     // priority-resolved colour classes (Stella 3.x encoder: PF priority disables score colouring)
@@ -396,11 +412,11 @@ __device__ __forceinline__ void render_to(Chip &s, const Tables &T, int x, uint8
         if (!(s.vblank & 2)) render_span<VERIFY>(s, T, s.rx, x, row, fb_row);
         // VBLANK: black; the framebuffer is pre-cleared to 0 and black matches no target channel
         // unless a target colour has a 0 channel, which accumulate_class would need to see:
-        else {
+        else if (row >= CROP_TOP && row < CROP_BOTTOM && T.weight[0]) {
             Masks R;
 #pragma unroll
             for (int i = 0; i < 5; ++i) R.w[i] = range_word(i, s.rx, x);
-            if (row >= CROP_TOP && row < CROP_BOTTOM) accumulate_class(s, T, 0, R, row - CROP_TOP);
+            accumulate_class(s, T, 0, R, row - CROP_TOP);
         }
     }
     s.rx = x;
@@ -422,11 +438,61 @@ __device__ __forceinline__ void tia_catchup(Chip &s, const Tables &T, int h, uin
 __device__ __forceinline__ int hm_signed(uint32_t hm) { int v = (int)(hm >> 4); return v >= 8 ? v - 16 : v; }
 __device__ __forceinline__ uint8_t wrap160(int v) { v %= 160; return (uint8_t)(v < 0 ? v + 160 : v); }
 
-// TIA register write.  cyc_after = CPU cycle count after the write cycle; hpos = colour clock
-// within the CPU's scanline.  Returns the number of cycles the CPU stalls (WSYNC).
-template <bool VERIFY>
-__device__ __noinline__ uint32_t tia_poke(Chip &s, const Tables &T, uint32_t reg, uint32_t v, uint32_t cyc_after, int hpos, uint8_t *fb)
+// Writes that need no catch-up of the lazy renderer: a write that leaves every visible latch as it was
+// cannot change a pixel; HMxx/HMCLR only matter at the next HMOVE; RSYNC/audio are ignored.  Returns
+// true when the write has been fully handled here.
+__device__ __forceinline__ bool poke_quick(Chip &s, uint32_t reg, uint32_t v)
 {
+    switch (reg) {
+    case 0x00: if (!((s.vsync & 2) && !(v & 2))) { s.vsync = (uint8_t)v; return true; } return false;
+    case 0x01: return v == s.vblank;
+    case 0x04: return v == s.nusiz0;
+    case 0x05: return v == s.nusiz1;
+    case 0x06: return v == s.colup0;
+    case 0x07: return v == s.colup1;
+    case 0x08: return v == s.colupf;
+    case 0x09: return v == s.colubk;
+    case 0x0A: return v == s.ctrlpf;
+    case 0x0B: return v == s.refp0;
+    case 0x0C: return v == s.refp1;
+    case 0x0D: return v == s.pf0;
+    case 0x0E: return v == s.pf1;
+    case 0x0F: return v == s.pf2;
+    case 0x1B: return v == s.grp0_new && s.grp1_old == s.grp1_new;
+    case 0x1C: return v == s.grp1_new && s.grp0_old == s.grp0_new && s.enabl_old == s.enabl_new;
+    case 0x1D: return v == s.enam0;
+    case 0x1E: return v == s.enam1;
+    case 0x1F: return v == s.enabl_new;
+    case 0x20: s.hmp0 = (uint8_t)v; return true;
+    case 0x21: s.hmp1 = (uint8_t)v; return true;
+    case 0x22: s.hmm0 = (uint8_t)v; return true;
+    case 0x23: s.hmm1 = (uint8_t)v; return true;
+    case 0x24: s.hmbl = (uint8_t)v; return true;
+    case 0x25: return v == s.vdelp0;
+    case 0x26: return v == s.vdelp1;
+    case 0x27: return v == s.vdelbl;
+    case 0x2B: s.hmp0 = s.hmp1 = s.hmm0 = s.hmm1 = s.hmbl = 0; return true;
+    case 0x03: case 0x15: case 0x16: case 0x17: case 0x18: case 0x19: case 0x1A: return true;
+    default: return reg > 0x2C;
+    }
+}
+
+// cycles the CPU parks after a WSYNC write that completed at cyc_after
+__device__ __forceinline__ uint32_t wsync_stall(uint32_t cyc_after, uint32_t cpu_ls)
+{
+    const uint32_t c = (cyc_after - cpu_ls) % LINE_CYCLES;
+    return c ? LINE_CYCLES - c : 0u;
+}
+
+// TIA register write.  cyc_after = CPU cycle count after the write cycle; cpu_ls = a CPU cycle at which
+// some scanline started (the colour clock within the line follows from their difference).  Returns the
+// number of cycles the CPU stalls (WSYNC).
+template <bool VERIFY>
+__device__ __noinline__ uint32_t tia_poke(Chip &s, const Tables &T, uint32_t reg, uint32_t v, uint32_t cyc_after, uint32_t cpu_ls, uint8_t *fb)
+{
+    if (reg == 0x02) return wsync_stall(cyc_after, cpu_ls);
+    if (poke_quick(s, reg, v)) return 0;
+    const int hpos = 3 * (int)((cyc_after - cpu_ls) % LINE_CYCLES);
     int delay = 0;
     switch (reg) {
     case 0x01: case 0x0B: case 0x0C: case 0x1B: case 0x1C: case 0x1D: case 0x1E: case 0x1F: delay = 1; break;
@@ -435,8 +501,6 @@ __device__ __noinline__ uint32_t tia_poke(Chip &s, const Tables &T, uint32_t reg
     default: break;
     }
     const int h = 3 * (int)(cyc_after - s.tia_ls) + delay;
-    // fast exits that need no catch-up: audio and unused registers
-    if ((reg >= 0x15 && reg <= 0x1A) || reg > 0x2C || reg == 0x03) return 0;
     tia_catchup<VERIFY>(s, T, h, fb);
     uint32_t stall = 0;
     switch (reg) {
@@ -453,7 +517,6 @@ __device__ __noinline__ uint32_t tia_poke(Chip &s, const Tables &T, uint32_t reg
         if ((s.vblank & 0x80) && !(v & 0x80)) { s.dump_enabled = 0; s.dump_cyc = cyc_after; }
         s.vblank = (uint8_t)v;
         break;
-    case 0x02: { int c = hpos / 3; if (c) stall = (uint32_t)(LINE_CYCLES - c); break; }
     case 0x04: s.nusiz0 = (uint8_t)v; break;
     case 0x05: s.nusiz1 = (uint8_t)v; break;
     case 0x06: s.colup0 = (uint8_t)v; break;
@@ -709,10 +772,10 @@ __device__ __forceinline__ void run_frame(Chip &s, CpuRegs &r, const Tables &T, 
                 // pushes go through the full bus (the stack pointer may sit in TIA space)
                 uint32_t sa = 0x100 | sp;
                 if ((sa & 0x1280) == 0x0080) ram.wr(sa, ret >> 8);
-                else if (!(sa & 0x1080)) stall += tia_poke<VERIFY>(s, T, sa & 0x3F, ret >> 8, cyc + 4, (int)(3 * ((cyc + 4 - cpu_ls) % LINE_CYCLES)), fb);
+                else if (!(sa & 0x1080)) stall += tia_poke<VERIFY>(s, T, sa & 0x3F, ret >> 8, cyc + 4, cpu_ls, fb);
                 sp = (sp - 1) & 0xFF; sa = 0x100 | sp;
                 if ((sa & 0x1280) == 0x0080) ram.wr(sa, ret & 0xFF);
-                else if (!(sa & 0x1080)) stall += tia_poke<VERIFY>(s, T, sa & 0x3F, ret & 0xFF, cyc + 5, (int)(3 * ((cyc + 5 - cpu_ls) % LINE_CYCLES)), fb);
+                else if (!(sa & 0x1080)) stall += tia_poke<VERIFY>(s, T, sa & 0x3F, ret & 0xFF, cyc + 5, cpu_ls, fb);
                 sp = (sp - 1) & 0xFF;
                 pc = ea;
                 break;
@@ -737,7 +800,7 @@ __device__ __forceinline__ void run_frame(Chip &s, CpuRegs &r, const Tables &T, 
                 for (int k = 0; k < 3; ++k) {
                     uint32_t sa = 0x100 | sp;
                     if ((sa & 0x1280) == 0x0080) ram.wr(sa, vals[k]);
-                    else if (!(sa & 0x1080)) stall += tia_poke<VERIFY>(s, T, sa & 0x3F, vals[k], cyc + 3 + k, (int)(3 * ((cyc + 3 + k - cpu_ls) % LINE_CYCLES)), fb);
+                    else if (!(sa & 0x1080)) stall += tia_poke<VERIFY>(s, T, sa & 0x3F, vals[k], cyc + 3 + k, cpu_ls, fb);
                     sp = (sp - 1) & 0xFF;
                 }
                 fid |= 4u;
@@ -760,10 +823,8 @@ __device__ __forceinline__ void run_frame(Chip &s, CpuRegs &r, const Tables &T, 
                 const uint32_t wa = ea & 0x1FFF;
                 const uint32_t t_after = cyc + ncyc;
                 if ((wa & 0x1280) == 0x0080) ram.wr(wa, wv);
-                else if (!(wa & 0x1080)) {
-                    uint32_t c = t_after - cpu_ls; if (c >= LINE_CYCLES) c -= LINE_CYCLES;
-                    stall += tia_poke<VERIFY>(s, T, wa & 0x3F, wv, t_after, (int)(3 * c), fb);
-                } else if ((wa & 0x1280) == 0x0280) riot_poke(s, wa, wv, t_after);
+                else if (!(wa & 0x1080)) stall += tia_poke<VERIFY>(s, T, wa & 0x3F, wv, t_after, cpu_ls, fb);
+                else if ((wa & 0x1280) == 0x0280) riot_poke(s, wa, wv, t_after);
             }
             cyc += ncyc + stall;
         }

@@ -3,7 +3,7 @@
 #include <stdint.h>
 #include <string.h>
 
-#include "a26_core.cuh"
+#include "a26_compiled.cuh"
 
 namespace ngp_host {
 
@@ -28,6 +28,7 @@ inline void build_tables(a26::Tables &tables, const uint8_t *rom, const uint8_t 
     a26::DecodeTable dt;
     a26::build_decode_table(dt);
     memcpy(tables.decode, dt.e, sizeof(dt.e));
+    a26::fill_blockmap(tables.blockmap);
     const uint8_t *targets[3] = {ball, left, right};
     for (int i = 0; i < 128; ++i) {
         uint32_t c = palette[i];

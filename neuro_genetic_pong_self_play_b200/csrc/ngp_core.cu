@@ -61,6 +61,7 @@ extern "C" void ngp_default_config(ngp_config *cfg, int32_t population)
     memcpy(cfg->ball_colour, ball, 3); memcpy(cfg->left_colour, left, 3); memcpy(cfg->right_colour, right, 3);
     cfg->cxpb = 0.9f; cfg->cx_alpha = 0.9f; cfg->mutpb = 0.9f; cfg->mut_mu = 0.0f; cfg->mut_sigma = 0.9f; cfg->mut_indpb = 0.9f;
     cfg->tournament_size = population / 4;
+    cfg->core = NGP_CORE_TRANSLATED;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -102,7 +103,7 @@ __global__ void env_reset_kernel(const Snapshot *start, Snapshot *envs, int n)
     if (i < n) envs[i] = *start;
 }
 
-__global__ void __launch_bounds__(32) env_step_kernel(const Tables *tables, const uint32_t *needed, Snapshot *envs, int n,
+__global__ void __launch_bounds__(32) env_step_kernel(const Tables *tables, const uint32_t *needed, Snapshot *envs, int n, int core,
                                                       const uint8_t *actions, uint8_t *fb, uint8_t *ram_out, float *loc,
                                                       uint8_t *valid, uint8_t *regs, unsigned long long *counters)
 {
@@ -118,7 +119,9 @@ __global__ void __launch_bounds__(32) env_step_kernel(const Tables *tables, cons
     action_to_input(actions + (size_t)e * 16, fire, dec, inc);
     a26::apply_input(s, needed, 0x3F, fire, dec, inc);
     a26::clear_obs(s);
-    a26::run_frame<true>(s, r, T, ram, fb ? fb + (size_t)e * a26::FB_ROWS * a26::FB_COLS : nullptr);
+    uint8_t *my_fb = fb ? fb + (size_t)e * a26::FB_ROWS * a26::FB_COLS : nullptr;
+    if (core) a26::run_frame_compiled<true>(s, r, T, ram, my_fb);
+    else a26::run_frame<true>(s, r, T, ram, my_fb);
     store_snapshot(&envs[e], s, r, ram);
     if (s.error) atomicAdd(&counters[2], 1ull);
     if (ram_out) for (int i = 0; i < 128; ++i) ram_out[(size_t)e * 128 + i] = (uint8_t)ram.rd(i);
@@ -300,6 +303,12 @@ extern "C" int ngp_env_reset(ngp_handle *h, int32_t n_envs, int32_t state_id, vo
 extern "C" int ngp_env_step(ngp_handle *h, const uint8_t *actions, uint8_t *ram, uint8_t *frames, float *loc, uint8_t *valid,
                             uint8_t *regs, void *stream)
 {
+    return ngp_env_step_core(h, NGP_CORE_INTERPRETER, actions, ram, frames, loc, valid, regs, stream);
+}
+
+extern "C" int ngp_env_step_core(ngp_handle *h, int32_t core, const uint8_t *actions, uint8_t *ram, uint8_t *frames, float *loc,
+                                 uint8_t *valid, uint8_t *regs, void *stream)
+{
     NGP_REQUIRE(h && actions, "ngp_env_step: bad arguments");
     NGP_REQUIRE(h->n_envs > 0, "ngp_env_step: call ngp_env_reset first");
     NGP_REQUIRE((loc == nullptr) == (valid == nullptr), "ngp_env_step: loc and valid go together");
@@ -308,7 +317,7 @@ extern "C" int ngp_env_step(ngp_handle *h, const uint8_t *actions, uint8_t *ram,
     const int n = h->n_envs;
     const size_t px = (size_t)n * a26::FB_ROWS * a26::FB_COLS;
     if (frames) NGP_CUDA(cudaMemsetAsync(h->d_fb, 0, px, st));
-    env_step_kernel<<<(n + 31) / 32, 32, 0, st>>>(h->d_tables, h->d_needed, h->d_envs, n, actions, frames ? h->d_fb : nullptr, ram,
+    env_step_kernel<<<(n + 31) / 32, 32, 0, st>>>(h->d_tables, h->d_needed, h->d_envs, n, core ? 1 : 0, actions, frames ? h->d_fb : nullptr, ram,
                                                   loc, valid, regs, h->d_counters);
     h->launches++;
     NGP_CUDA(cudaGetLastError());
@@ -361,6 +370,7 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
     p.tables = h->d_tables; p.needed = h->d_needed; p.start = h->d_start;
     p.genomes = genomes; p.hof_genomes = hof_genomes; p.hof_fitness = hof_fitness; p.hof_pick = hof_pick;
     p.n = n; p.n_hof = n_hof; p.G = h->gene_size; p.games = games; p.schedule = h->cfg.schedule;
+    p.core = h->cfg.core ? 1 : 0;
     p.win_score = h->cfg.win_score; p.timeout_thresh = h->cfg.timeout_thresh; p.max_frames = h->cfg.max_frames;
     p.time_scaler = (double)h->cfg.time_scaler; p.paddle_height = (double)h->cfg.scaled_paddle_height;
     p.seed = seed; p.generation = generation; p.shape = h->shape;

@@ -4,7 +4,7 @@
 // main.get_actions 138-154, main.calculate_timeout_and_frames 128-135, utils.calculate_reward 104-109.
 #pragma once
 #include "../../include/ngp.h"
-#include "a26_core.cuh"
+#include "a26_compiled.cuh"
 #include "policy.cuh"
 
 namespace roll {
@@ -71,6 +71,7 @@ struct RolloutParams {
     const double *hof_fitness;      // [n_hof]
     const int32_t *hof_pick;        // [n][3] or null
     int n, n_hof, G, games, schedule, win_score, timeout_thresh, max_frames;
+    int core;                       // 0 = table-driven interpreter, 1 = statically translated cartridge
     double time_scaler, paddle_height;
     uint64_t seed, generation;
     pol::Shape shape;
@@ -159,7 +160,8 @@ __device__ __forceinline__ bool episode_frame(Episode &ep, const RolloutParams &
     acts_to_input(ep.left_act, ep.right_act, fire, dec, inc);
     a26::apply_input(s, p.needed, 0x3F, fire, dec, inc);
     a26::clear_obs(s);
-    a26::run_frame<false>(s, r, T, ram, nullptr);
+    if (p.core) a26::run_frame_compiled<false>(s, r, T, ram, nullptr);
+    else a26::run_frame<false>(s, r, T, ram, nullptr);
     const int s1 = (int)ram.rd(13), s2 = (int)ram.rd(14);          // score1 = $8D, score2 = $8E
     // ---- observation (find_stuff) ----
     bool valid[3]; double loc[3][2];

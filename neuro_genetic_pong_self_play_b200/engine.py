@@ -82,7 +82,7 @@ class Engine:
         _lib.check(self._L.ngp_env_reset(self._h, n_envs, state, _stream(self.device)), "ngp_env_reset")
         self._n_envs = n_envs
 
-    def env_step(self, actions: torch.Tensor, want_frames: bool = True, want_obs: bool = True):
+    def env_step(self, actions: torch.Tensor, want_frames: bool = True, want_obs: bool = True, core: int = _lib.CORE_INTERPRETER):
         """actions: u8[n_envs,16] gym-retro buttons.  Returns dict(ram, frames, loc, valid, regs)."""
         n = self._n_envs
         self._check_tensor(actions, torch.uint8, "actions")
@@ -94,8 +94,8 @@ class Engine:
             "loc": torch.empty((n, 3, 2), dtype=torch.float32, device=self.device) if want_obs else None,
             "valid": torch.empty((n, 3), dtype=torch.uint8, device=self.device) if want_obs else None,
         }
-        _lib.check(self._L.ngp_env_step(self._h, _p(actions), _p(out["ram"]), _p(out["frames"]), _p(out["loc"]), _p(out["valid"]),
-                                        _p(out["regs"]), _stream(self.device)), "ngp_env_step")
+        _lib.check(self._L.ngp_env_step_core(self._h, core, _p(actions), _p(out["ram"]), _p(out["frames"]), _p(out["loc"]),
+                                             _p(out["valid"]), _p(out["regs"]), _stream(self.device)), "ngp_env_step")
         return out
 
     def env_digest(self) -> torch.Tensor:

@@ -96,7 +96,7 @@ void hs_env_power_on(void *h)
 }
 
 // raw console input step (like a26o_run_frame)
-int hs_env_run_frame(void *h, int swchb, int fire, int dec, int inc, uint8_t *ram_out, uint8_t *fb, double *loc, uint8_t *valid,
+int hs_env_run_frame(void *h, int core, int swchb, int fire, int dec, int inc, uint8_t *ram_out, uint8_t *fb, double *loc, uint8_t *valid,
                      uint8_t *regs, uint32_t *digest)
 {
     Sim *sim = (Sim *)h;
@@ -105,7 +105,8 @@ int hs_env_run_frame(void *h, int swchb, int fire, int dec, int inc, uint8_t *ra
     a26::apply_input(s, sim->needed.data(), (uint32_t)swchb, (uint32_t)fire, (uint32_t)dec, (uint32_t)inc);
     a26::clear_obs(s);
     if (fb) memset(fb, 0, 210 * 160);
-    a26::run_frame<true>(s, sim->r, sim->T, ram, fb);
+    if (core) a26::run_frame_compiled<true>(s, sim->r, sim->T, ram, fb);
+    else a26::run_frame<true>(s, sim->r, sim->T, ram, fb);
     if (ram_out) for (int i = 0; i < 128; ++i) ram_out[i] = (uint8_t)ram.rd(i);
     if (loc && valid)
         for (int t = 0; t < 3; ++t) {
@@ -131,15 +132,15 @@ int hs_env_run_frame(void *h, int swchb, int fire, int dec, int inc, uint8_t *ra
     return s.error;
 }
 
-int hs_env_step(void *h, const uint8_t *action16, uint8_t *ram_out, uint8_t *fb, double *loc, uint8_t *valid, uint8_t *regs, uint32_t *digest)
+int hs_env_step(void *h, int core, const uint8_t *action16, uint8_t *ram_out, uint8_t *fb, double *loc, uint8_t *valid, uint8_t *regs, uint32_t *digest)
 {
     uint32_t fire, dec, inc;
     roll::action_to_input(action16, fire, dec, inc);
-    return hs_env_run_frame(h, 0x3F, (int)fire, (int)dec, (int)inc, ram_out, fb, loc, valid, regs, digest);
+    return hs_env_run_frame(h, core, 0x3F, (int)fire, (int)dec, (int)inc, ram_out, fb, loc, valid, regs, digest);
 }
 
 // fused evaluation, lanes executed one after another
-void hs_evaluate(void *h, const int32_t *nodes, int n_layers, int bias, int schedule, int games, int max_frames, const float *genomes, int n,
+void hs_evaluate(void *h, int core, const int32_t *nodes, int n_layers, int bias, int schedule, int games, int max_frames, const float *genomes, int n,
                  const float *hof_genomes, const double *hof_fitness, int n_hof, const int32_t *hof_pick, uint64_t seed,
                  uint64_t generation, double *rewards, int32_t *frames)
 {
@@ -149,7 +150,7 @@ void hs_evaluate(void *h, const int32_t *nodes, int n_layers, int bias, int sche
     p.tables = &sim->T; p.needed = sim->needed.data(); p.start = sim->start;
     p.genomes = genomes; p.hof_genomes = hof_genomes; p.hof_fitness = hof_fitness; p.hof_pick = hof_pick;
     p.n = n; p.n_hof = n_hof; p.games = games; p.schedule = schedule; p.win_score = 3; p.timeout_thresh = 2000; p.max_frames = max_frames;
-    p.time_scaler = 100.0; p.paddle_height = 16.0; p.seed = seed; p.generation = generation;
+    p.core = core; p.time_scaler = 100.0; p.paddle_height = 16.0; p.seed = seed; p.generation = generation;
     p.shape.n_layers = n_layers; p.shape.bias = bias;
     int G = 0;
     for (int i = 0; i < n_layers; ++i) p.shape.nodes[i] = nodes[i];

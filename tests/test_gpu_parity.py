@@ -56,8 +56,9 @@ def _oracle_trace(args):
     return ram, regs, dig, crc, loc, valid
 
 
-def test_env_step_trace_parity(engine):
-    """RAM, CPU registers, TIA digest (collision latches, positions, paddle charges), every frame
+@pytest.mark.parametrize("core", [0, 1])
+def test_env_step_trace_parity(engine, core):
+    """core 0 = table-driven interpreter, core 1 = statically translated cartridge.  RAM, CPU registers, TIA digest (collision latches, positions, paddle charges), every frame
     (CRC of the RGB frame) and the fused find_stuff result, frame by frame, on random action traces
     from both start states (BASELINE config 2's bit-exact RAM/frame check)."""
     n_envs, n_frames = 16, 1200
@@ -71,7 +72,7 @@ def test_env_step_trace_parity(engine):
         engine.env_reset(len(idx), state)
         for f in range(n_frames):
             a = torch.from_numpy(np.stack([acts[i][f] for i in idx])).cuda()
-            out = engine.env_step(a)
+            out = engine.env_step(a, core=core)
             ram = out["ram"].cpu().numpy(); regs = out["regs"].cpu().numpy(); frames = out["frames"].cpu().numpy()
             loc = out["loc"].cpu().numpy(); valid = out["valid"].cpu().numpy(); dig = engine.env_digest().cpu().numpy().view(np.uint32)
             for j, i in enumerate(idx):
@@ -125,6 +126,12 @@ def test_fused_evaluate_reference_schedule_parity(ngp, engine):
         assert np.array_equal(rewards[g], r), (g, rewards[g], r)
         assert fitness[g] == fit
     assert out["frames_total"] == int(frames.sum())
+    # the interpreter core gives the same bits as the translated core
+    eng_i = ngp.Engine(ngp.Config(CORE=ngp.CORE_INTERPRETER), device=0)
+    out_i = eng_i.evaluate(torch.from_numpy(genomes).cuda(), torch.from_numpy(hof).cuda(), torch.from_numpy(hof_fit).cuda(),
+                           torch.from_numpy(pick).cuda(), seed=11, generation=0, want_detail=True)
+    assert torch.equal(out_i["rewards"], out["rewards"]) and torch.equal(out_i["frames"], out["frames"])
+    eng_i.close()
     # no hall of fame: games 3..5 fall back to HardcodedAi with multiplier 1 (main.py:43-53)
     out2 = engine.evaluate(torch.from_numpy(genomes[:2]).cuda(), seed=11, want_detail=True)
     for g in range(2):

@@ -23,8 +23,8 @@ def hs():
     L.hs_create.restype = vp
     L.hs_env_reset.argtypes = [vp, ctypes.c_int]
     L.hs_env_power_on.argtypes = [vp]
-    L.hs_env_step.argtypes = [vp] * 8
-    L.hs_evaluate.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, vp,
+    L.hs_env_step.argtypes = [vp, ctypes.c_int] + [vp] * 7
+    L.hs_evaluate.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, vp,
                               ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_uint64, vp, vp]
     return L, vp(L.hs_create(oracle.load_rom()))
 
@@ -33,8 +33,10 @@ def P(a):
     return a.ctypes.data_as(vp)
 
 
+@pytest.mark.parametrize("core", [0, 1])
 @pytest.mark.parametrize("state,frames,hold", [(None, 120, 3), (0, 500, 4), (1, 700, 7)])
-def test_core_matches_oracle_on_random_traces(hs, state, frames, hold):
+def test_core_matches_oracle_on_random_traces(hs, state, frames, hold, core):
+    """core 0 = table-driven interpreter, core 1 = statically translated cartridge."""
     L, sim = hs
     rng = np.random.RandomState(frames)
     env = oracle.Atari()
@@ -51,7 +53,7 @@ def test_core_matches_oracle_on_random_traces(hs, state, frames, hold):
             r, l = rng.randint(0, 3), rng.randint(0, 3)
             act[4] = r == 1; act[5] = r == 2; act[6] = l == 1; act[7] = l == 2
         ofb = env.step(act)
-        assert L.hs_env_step(sim, P(act), P(ram), P(fb), P(loc), P(valid), P(regs), P(dig)) == 0
+        assert L.hs_env_step(sim, core, P(act), P(ram), P(fb), P(loc), P(valid), P(regs), P(dig)) == 0
         assert np.array_equal(env.ram, ram), f
         assert np.array_equal(env.cpu_regs[:7], regs[:7]), f
         assert np.array_equal(ofb, fb), f
@@ -60,7 +62,8 @@ def test_core_matches_oracle_on_random_traces(hs, state, frames, hold):
         assert np.array_equal(ov, valid) and np.array_equal(ol[ov == 1].ravel(), loc.reshape(3, 2)[valid == 1].ravel()), f
 
 
-def test_fused_rollout_matches_oracle_evaluate(hs):
+@pytest.mark.parametrize("core", [0, 1])
+def test_fused_rollout_matches_oracle_evaluate(hs, core):
     L, sim = hs
     rng = np.random.RandomState(7)
     nodes = np.array([6, 2, 2], np.int32)
@@ -68,6 +71,6 @@ def test_fused_rollout_matches_oracle_evaluate(hs):
     hof = (rng.random_sample((3, 20)) * 4 - 2).astype(np.float32); hof_fit = np.array([0.7, 0.3, 0.1])
     pick = np.array([[2, 0, 1]], np.int32)
     rew = np.zeros((1, 6)); frm = np.zeros((1, 6), np.int32)
-    L.hs_evaluate(sim, P(nodes), 3, 1, 0, 6, 0, P(genomes), 1, P(hof), P(hof_fit), 3, P(pick), 5, 0, P(rew), P(frm))
+    L.hs_evaluate(sim, core, P(nodes), 3, 1, 0, 6, 0, P(genomes), 1, P(hof), P(hof_fit), 3, P(pick), 5, 0, P(rew), P(frm))
     fit, r, f = oracle.evaluate([6, 2, 2], genomes[0], hof, hof_fit, pick[0], seed=5, genome_id=0)
     assert np.array_equal(r, rew[0]) and np.array_equal(f, frm[0])
