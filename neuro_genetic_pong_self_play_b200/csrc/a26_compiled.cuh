@@ -65,7 +65,9 @@ __device__ __forceinline__ void run_frame_compiled(Chip &s, CpuRegs &r, const Ta
     while (!done && (cyc - start_cyc) < FRAME_CYCLE_CAP) {
         const uint32_t line_end = cpu_ls + LINE_CYCLES;
         while ((int32_t)(cyc - line_end) < 0 && !done) {
+            A26_STAT(5);
             const uint32_t entry = (pc & 0x1000u) ? T.blockmap[pc & 0x7FFu] : 0u;
+            A26_STAT_ENTRY(pc);
             switch (entry) {
 #include "generated/pong_core.inc"
             default:
@@ -73,6 +75,7 @@ __device__ __forceinline__ void run_frame_compiled(Chip &s, CpuRegs &r, const Ta
                 done = 1;
                 break;
             }
+        a26_next_:;
         }
         while ((int32_t)(cyc - (cpu_ls + LINE_CYCLES)) >= 0) cpu_ls += LINE_CYCLES;
     }

@@ -18,6 +18,17 @@
 #pragma once
 #include <stdint.h>
 
+// optional event counters for the CPU-side debugging harness (tests/host_sim): no code unless A26_STATS
+#ifdef A26_STATS
+extern unsigned long long a26_stats[16];
+extern unsigned long long a26_entry_stats[2048];
+#define A26_STAT(i) (++a26_stats[i])
+#define A26_STAT_ENTRY(pc) (++a26_entry_stats[(pc) & 0x7FF])
+#else
+#define A26_STAT(i) ((void)0)
+#define A26_STAT_ENTRY(pc) ((void)0)
+#endif
+
 namespace a26 {
 
 // ---- Stella-convention constants (named, swappable; DESIGN.md "Emulator spec") -----------------
@@ -293,24 +304,106 @@ __device__ __forceinline__ void accumulate_class(Chip &s, const Tables &T, uint3
     }
 }
 
-// Render pixels [x0, x1) of the TIA's current scanline (display row `row`), VBLANK off.
-template <bool VERIFY>
-__device__ __noinline__ void render_span(Chip &s, const Tables &T, int x0, int x1, int row, uint8_t *fb_row)
+// Fast accounting of a span in the fused (no framebuffer) mode.  Returns true when the span needs no
+// mask rendering: (A) no movable object is enabled -- no collision is possible and only playfield /
+// background colours could contribute to the observation; (B) the playfield is empty and the enabled
+// objects are single copies whose boxes do not overlap -- no collision, every object pixel shows its own
+// colour, so its observation sums follow from the object's pattern directly.  Anything else (playfield
+// with objects, overlapping boxes, multi-copy NUSIZ modes, wrap-around, a background colour that matches
+// a target channel, the HMOVE comb) goes through render_span.
+struct QuickObj { int start, width; uint32_t pat, colour; };
+__device__ __forceinline__ bool quick_player(QuickObj &o, uint32_t grp, uint32_t nusiz, uint32_t pos, bool reflect, bool suppress, uint32_t colour, bool &fail)
+{
+    if (!grp || suppress) return false;
+    const uint32_t mode = nusiz & 7;
+    uint32_t pat = reflect ? grp : (__brev(grp) >> 24);
+    int start = (int)pos, width = 8;
+    if (mode == 5) { pat = expand2(pat); start += 1; width = 16; }
+    else if (mode == 7) { pat = expand4(pat); start += 1; width = 32; }
+    else if (mode != 0) { fail = true; return false; }
+    if (start + width > 160) { fail = true; return false; }
+    o.start = start; o.width = width; o.pat = pat; o.colour = colour;
+    return true;
+}
+__device__ __forceinline__ bool quick_missile(QuickObj &o, uint32_t nusiz, uint32_t pos, uint32_t colour, bool &fail)
+{
+    const uint32_t mode = nusiz & 7;
+    if (mode != 0 && mode != 5 && mode != 7) { fail = true; return false; }
+    const int width = 1 << ((nusiz >> 4) & 3);
+    if ((int)pos + width > 160) { fail = true; return false; }
+    o.start = (int)pos; o.width = width; o.pat = (1u << width) - 1u; o.colour = colour;
+    return true;
+}
+static __device__ __noinline__ bool render_span_quick(Chip &s, const Tables &T, int x0, int x1, int row)
 {
     const uint32_t grp0 = (s.vdelp0 & 1) ? s.grp0_old : s.grp0_new, grp1 = (s.vdelp1 & 1) ? s.grp1_old : s.grp1_new;
     const bool bl_on = (((s.vdelbl & 1) ? s.enabl_old : s.enabl_new) & 2) != 0;
     const bool m0_on = (s.enam0 & 2) && !(s.resmp0 & 2), m1_on = (s.enam1 & 2) && !(s.resmp1 & 2);
-    const bool in_crop_row = row >= CROP_TOP && row < CROP_BOTTOM;
+    const bool in_crop = row >= CROP_TOP && row < CROP_BOTTOM;
+    const bool pf_any = (s.pfmask[0] | s.pfmask[1] | s.pfmask[2] | s.pfmask[3] | s.pfmask[4]) != 0;
+    const bool comb = s.hmove_blank && x0 < 8;
     if (!(grp0 | grp1) && !bl_on && !m0_on && !m1_on) {
-        // only playfield and background on this span: no collision is possible
-        if (!VERIFY) {
-            if (!in_crop_row) return;
-            uint32_t wts = T.weight[s.colupf >> 1] | T.weight[s.colubk >> 1];
-            if (s.ctrlpf & 2) wts |= T.weight[s.colup0 >> 1] | T.weight[s.colup1 >> 1];
-            if (s.hmove_blank) wts |= T.weight[0];
-            if (!wts) return;                      // none of these colours shares a channel with a target colour
+        if (!in_crop) return true;
+        uint32_t wts = T.weight[s.colubk >> 1];
+        if (pf_any) {
+            wts |= T.weight[s.colupf >> 1];
+            if ((s.ctrlpf & 6) == 2) wts |= T.weight[s.colup0 >> 1] | T.weight[s.colup1 >> 1];
+        }
+        if (comb) wts |= T.weight[0];
+        return wts == 0;
+    }
+    if (pf_any || comb || T.weight[s.colubk >> 1]) return false;
+    QuickObj o[5];
+    bool on[5], fail = false;
+    on[0] = quick_player(o[0], grp0, s.nusiz0, s.posp0, (s.refp0 & 8) != 0, (s.suppress & 1) != 0, s.colup0, fail);
+    on[1] = quick_player(o[1], grp1, s.nusiz1, s.posp1, (s.refp1 & 8) != 0, (s.suppress & 2) != 0, s.colup1, fail);
+    on[2] = m0_on && quick_missile(o[2], s.nusiz0, s.posm0, s.colup0, fail);
+    on[3] = m1_on && quick_missile(o[3], s.nusiz1, s.posm1, s.colup1, fail);
+    on[4] = false;
+    if (bl_on) {
+        const int width = 1 << ((s.ctrlpf >> 4) & 3);
+        if ((int)s.posbl + width > 160) fail = true;
+        else { o[4].start = s.posbl; o[4].width = width; o[4].pat = (1u << width) - 1u; o[4].colour = s.colupf; on[4] = true; }
+    }
+    if (fail) return false;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+        for (int j = i + 1; j < 5; ++j)
+            if (on[i] && on[j] && o[i].start < o[j].start + o[j].width && o[j].start < o[i].start + o[i].width) return false;
+    if (!in_crop) return true;
+    const uint32_t cr = (uint32_t)(row - CROP_TOP);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        if (!on[i]) continue;
+        const uint32_t wts = T.weight[o[i].colour >> 1];
+        if (!wts) continue;
+        int lo = x0 - o[i].start, hi = x1 - o[i].start;
+        lo = lo < 0 ? 0 : lo; hi = hi > o[i].width ? o[i].width : hi;
+        if (hi <= lo) continue;
+        const uint32_t clip = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+        const uint32_t q = o[i].pat & clip;
+        if (!q) continue;
+        const uint32_t n = __popc(q), sx = n * (uint32_t)o[i].start + bit_index_sum(q);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const uint32_t w = (wts >> (2 * t)) & 3;
+            s.cnt[t] += w * n; s.sx[t] += w * sx; s.sy[t] += w * n * cr;
         }
     }
+    return true;
+}
+
+// Render pixels [x0, x1) of the TIA's current scanline (display row `row`), VBLANK off.
+template <bool VERIFY>
+__device__ __noinline__ void render_span(Chip &s, const Tables &T, int x0, int x1, int row, uint8_t *fb_row)
+{
+    A26_STAT(2);
+    const uint32_t grp0 = (s.vdelp0 & 1) ? s.grp0_old : s.grp0_new, grp1 = (s.vdelp1 & 1) ? s.grp1_old : s.grp1_new;
+    const bool bl_on = (((s.vdelbl & 1) ? s.enabl_old : s.enabl_new) & 2) != 0;
+    const bool m0_on = (s.enam0 & 2) && !(s.resmp0 & 2), m1_on = (s.enam1 & 2) && !(s.resmp1 & 2);
+    const bool in_crop_row = row >= CROP_TOP && row < CROP_BOTTOM;
+    A26_STAT(3);
     Masks R, PF, BL, P0, P1, M0, M1;
 #pragma unroll
     for (int i = 0; i < 5; ++i) { R.w[i] = range_word(i, x0, x1); PF.w[i] = s.pfmask[i] & R.w[i]; }
@@ -409,7 +502,9 @@ __device__ __forceinline__ void render_to(Chip &s, const Tables &T, int x, uint8
     int row = s.line - YSTART;
     if (row >= 0 && row < FB_ROWS) {
         uint8_t *fb_row = (VERIFY && fb) ? fb + row * FB_COLS : nullptr;
-        if (!(s.vblank & 2)) render_span<VERIFY>(s, T, s.rx, x, row, fb_row);
+        if (!(s.vblank & 2)) {
+            if (VERIFY || !render_span_quick(s, T, s.rx, x, row)) render_span<VERIFY>(s, T, s.rx, x, row, fb_row);
+        }
         // VBLANK: black; the framebuffer is pre-cleared to 0 and black matches no target channel
         // unless a target colour has a 0 channel, which accumulate_class would need to see:
         else if (row >= CROP_TOP && row < CROP_BOTTOM && T.weight[0]) {
@@ -490,8 +585,10 @@ __device__ __forceinline__ uint32_t wsync_stall(uint32_t cyc_after, uint32_t cpu
 template <bool VERIFY>
 __device__ __noinline__ uint32_t tia_poke(Chip &s, const Tables &T, uint32_t reg, uint32_t v, uint32_t cyc_after, uint32_t cpu_ls, uint8_t *fb)
 {
+    A26_STAT(0);
     if (reg == 0x02) return wsync_stall(cyc_after, cpu_ls);
     if (poke_quick(s, reg, v)) return 0;
+    A26_STAT(1);
     const int hpos = 3 * (int)((cyc_after - cpu_ls) % LINE_CYCLES);
     int delay = 0;
     switch (reg) {
@@ -570,22 +667,28 @@ __device__ __noinline__ uint32_t tia_poke(Chip &s, const Tables &T, uint32_t reg
     return stall;
 }
 
+// collision latch read: needs the renderer caught up to the read
 template <bool VERIFY>
-__device__ __noinline__ uint32_t tia_peek(Chip &s, const Tables &T, uint32_t reg, uint32_t cyc_after, uint32_t dbus, uint8_t *fb)
+__device__ __noinline__ uint32_t tia_peek_cx(Chip &s, const Tables &T, uint32_t reg, uint32_t cyc_after, uint8_t *fb)
 {
-    uint32_t noise = dbus & 0x3F;
+    tia_catchup<VERIFY>(s, T, 3 * (int)(cyc_after - s.tia_ls), fb);
+    uint32_t v = (((s.cx >> (2 * reg + 1)) & 1u) << 7) | (((s.cx >> (2 * reg)) & 1u) << 6);
+    if (reg == 6) v &= 0x80;
+    return v;
+}
+
+template <bool VERIFY>
+__device__ __forceinline__ uint32_t tia_peek(Chip &s, const Tables &T, uint32_t reg, uint32_t cyc_after, uint32_t dbus, uint8_t *fb)
+{
+    A26_STAT(4);
+    const uint32_t noise = dbus & 0x3F;
     reg &= 0x0F;
-    if (reg < 8) {
-        tia_catchup<VERIFY>(s, T, 3 * (int)(cyc_after - s.tia_ls), fb);
-        uint32_t v = (((s.cx >> (2 * reg + 1)) & 1u) << 7) | (((s.cx >> (2 * reg)) & 1u) << 6);
-        if (reg == 6) v &= 0x80;
-        return v | noise;
-    }
-    if (reg < 12) {
+    if (reg >= 8 && reg < 12) {                       // INPT0-3: paddle capacitors (the hot case: 182 reads per frame)
         if (s.dump_enabled) return noise;
         return ((cyc_after - s.dump_cyc) > s.needed[reg - 8] ? 0x80u : 0u) | noise;
     }
-    if (reg < 14) return 0x80u | noise;
+    if (reg < 8) return tia_peek_cx<VERIFY>(s, T, reg, cyc_after, fb) | noise;
+    if (reg < 14) return 0x80u | noise;               // INPT4/5: joystick triggers, never pressed
     return noise;
 }
 

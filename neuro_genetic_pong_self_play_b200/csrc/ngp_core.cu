@@ -165,6 +165,7 @@ __global__ void env_digest_kernel(const Snapshot *envs, int n, uint32_t *out)
 // Fused rollout: one environment (= one game of one genome) per thread.  Lanes are persistent and
 // pull the next environment from a global counter at frame boundaries, so a warp stays in
 // scanline lock-step whatever episode each of its lanes is in.
+template <int CORE>
 __global__ void rollout_kernel(RolloutParams p)
 {
     __shared__ Tables T;
@@ -187,7 +188,7 @@ __global__ void rollout_kernel(RolloutParams p)
         if (__all_sync(0xFFFFFFFFu, ep.env < 0)) break;
         if (ep.env >= 0) {
             double reward;
-            const bool done = roll::episode_frame(ep, p, s, r, T, ram, &reward);
+            const bool done = roll::episode_frame<CORE>(ep, p, s, r, T, ram, &reward);
             my_frames++;
             if (done) {
                 p.rewards[ep.env] = reward;
@@ -383,7 +384,8 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
     long long blocks = (total + block - 1) / block;
     const size_t smem = (size_t)block * 32 * 4;
     int per_sm = 0;
-    NGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rollout_kernel, block, smem));
+    auto kernel = p.core ? rollout_kernel<1> : rollout_kernel<0>;
+    NGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
     if (per_sm < 1) per_sm = 1;
     const long long resident = (long long)per_sm * h->sm_count;
     if (blocks > resident) blocks = resident;            // persistent lanes pull the rest from the queue
@@ -399,7 +401,7 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
         h->prof_used++;
         NGP_CUDA(cudaEventRecord(ev0, st));
     }
-    rollout_kernel<<<(unsigned)blocks, block, smem, st>>>(p);
+    kernel<<<(unsigned)blocks, block, smem, st>>>(p);
     h->launches++;
     NGP_CUDA(cudaGetLastError());
     if (ev1) NGP_CUDA(cudaEventRecord(ev1, st));

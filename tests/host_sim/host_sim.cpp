@@ -132,6 +132,27 @@ int hs_env_run_frame(void *h, int core, int swchb, int fire, int dec, int inc, u
     return s.error;
 }
 
+// the fused (no framebuffer) flavour of one frame: what rollout_kernel executes
+int hs_env_step_fast(void *h, int core, const uint8_t *action16, uint8_t *ram_out, double *loc, uint8_t *valid)
+{
+    Sim *sim = (Sim *)h;
+    a26::Ram ram{sim->ram_words};
+    a26::Chip &s = sim->s;
+    uint32_t fire, dec, inc;
+    roll::action_to_input(action16, fire, dec, inc);
+    a26::apply_input(s, sim->needed.data(), 0x3F, fire, dec, inc);
+    a26::clear_obs(s);
+    if (core) a26::run_frame_compiled<false>(s, sim->r, sim->T, ram, nullptr);
+    else a26::run_frame<false>(s, sim->r, sim->T, ram, nullptr);
+    for (int i = 0; i < 128; ++i) ram_out[i] = (uint8_t)ram.rd(i);
+    for (int t = 0; t < 3; ++t) {
+        valid[t] = s.cnt[t] > 0;
+        loc[2 * t] = s.cnt[t] ? (double)s.sy[t] / (double)s.cnt[t] : 0.0;
+        loc[2 * t + 1] = s.cnt[t] ? (double)s.sx[t] / (double)s.cnt[t] : 0.0;
+    }
+    return s.error;
+}
+
 int hs_env_step(void *h, int core, const uint8_t *action16, uint8_t *ram_out, uint8_t *fb, double *loc, uint8_t *valid, uint8_t *regs, uint32_t *digest)
 {
     uint32_t fire, dec, inc;
@@ -163,7 +184,8 @@ void hs_evaluate(void *h, int core, const int32_t *nodes, int n_layers, int bias
         a26::Chip s; a26::CpuRegs r;
         roll::episode_begin(ep, p, e, s, r, ram);
         double reward = 0.0;
-        while (!roll::episode_frame(ep, p, s, r, sim->T, ram, &reward)) {}
+        if (core) { while (!roll::episode_frame<1>(ep, p, s, r, sim->T, ram, &reward)) {} }
+        else { while (!roll::episode_frame<0>(ep, p, s, r, sim->T, ram, &reward)) {} }
         rewards[e] = reward; frames[e] = ep.frame;
     }
 }

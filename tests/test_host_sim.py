@@ -24,6 +24,7 @@ def hs():
     L.hs_env_reset.argtypes = [vp, ctypes.c_int]
     L.hs_env_power_on.argtypes = [vp]
     L.hs_env_step.argtypes = [vp, ctypes.c_int] + [vp] * 7
+    L.hs_env_step_fast.argtypes = [vp, ctypes.c_int] + [vp] * 4
     L.hs_evaluate.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, vp,
                               ctypes.c_int, vp, ctypes.c_uint64, ctypes.c_uint64, vp, vp]
     return L, vp(L.hs_create(oracle.load_rom()))
@@ -74,3 +75,25 @@ def test_fused_rollout_matches_oracle_evaluate(hs, core):
     L.hs_evaluate(sim, core, P(nodes), 3, 1, 0, 6, 0, P(genomes), 1, P(hof), P(hof_fit), 3, P(pick), 5, 0, P(rew), P(frm))
     fit, r, f = oracle.evaluate([6, 2, 2], genomes[0], hof, hof_fit, pick[0], seed=5, genome_id=0)
     assert np.array_equal(r, rew[0]) and np.array_equal(f, frm[0])
+
+
+@pytest.mark.parametrize("core", [0, 1])
+def test_fused_mode_observation_matches_oracle(hs, core):
+    """The no-framebuffer flavour (quick span accounting, what rollout_kernel runs): RAM and the
+    find_stuff result of every frame against the oracle's frame + restated find_stuff."""
+    L, sim = hs
+    rng = np.random.RandomState(99 + core)
+    for state in (0, 1):
+        env = oracle.Atari(); env.reset_to_state(state); L.hs_env_reset(sim, state)
+        ram = np.zeros(128, np.uint8); loc = np.zeros(6); valid = np.zeros(3, np.uint8)
+        act = np.zeros(16, np.uint8)
+        for f in range(900):
+            if f % 5 == 0:
+                act = np.zeros(16, np.uint8); act[0] = act[15] = 1
+                r, l = rng.randint(0, 3), rng.randint(0, 3)
+                act[4] = r == 1; act[5] = r == 2; act[6] = l == 1; act[7] = l == 2
+            ofb = env.step(act)
+            assert L.hs_env_step_fast(sim, core, P(act), P(ram), P(loc), P(valid)) == 0
+            assert np.array_equal(env.ram, ram), f
+            ol, ov = oracle.find_stuff(oracle.fb_to_rgb(ofb))
+            assert np.array_equal(ov, valid) and np.array_equal(ol[ov == 1].ravel(), loc.reshape(3, 2)[valid == 1].ravel()), f

@@ -12,6 +12,7 @@ bit-for-bit against the CPU oracle.
 Usage: python tools/gen_rom_core.py        (rewrites the .inc next to the other CUDA sources)
 """
 import os
+import re
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -28,6 +29,7 @@ BRANCH = {"BPL": ("((nv >> 7) & 1u)", 0), "BMI": ("((nv >> 7) & 1u)", 1), "BVC":
           "BCC": ("fc", 0), "BCS": ("fc", 1), "BNE": ("(((zv & 0xFFu) == 0u) ? 1u : 0u)", 0),
           "BEQ": ("(((zv & 0xFFu) == 0u) ? 1u : 0u)", 1)}
 PAGE_PENALTY = {"abx", "aby", "izy"}          # only for read instructions
+MAX_STRUCTURED_SKIP = 24                      # bytes a structured forward branch may skip
 
 
 def load_rom():
@@ -52,6 +54,7 @@ def traverse(rom):
         seeds.add(0xF300 | rb(rom, base + 6))
         seeds.add(0xF300 | rb(rom, base + 8))
     instrs, leaders = {}, set(seeds)
+    fwd_branches = {}          # pc -> target, forward conditional branches (candidates for structured emission)
     work = list(seeds)
     while work:
         pc = work.pop()
@@ -69,7 +72,11 @@ def traverse(rom):
             if mode == "rel":
                 off = rb(rom, pc + 1)
                 t = (nxt + (off - 256 if off > 127 else off)) & 0xFFFF
-                leaders.add(t); work.append(t)
+                work.append(t)
+                if t > nxt and t - nxt <= MAX_STRUCTURED_SKIP:
+                    fwd_branches[pc] = t
+                else:
+                    leaders.add(t)
             elif mn == "JMP" and mode == "abs":
                 t = rb(rom, pc + 1) | rb(rom, pc + 2) << 8
                 leaders.add(t); work.append(t)
@@ -95,7 +102,37 @@ def traverse(rom):
     for a in instrs:
         if 0xF337 <= a <= 0xF41F:
             leaders.add(a)
-    return instrs, leaders
+    # Forward branches over a short, leader-free, properly nested run of instructions are emitted as
+    # structured if/else (no trip through the dispatcher, natural SIMT re-convergence).  Fixpoint: a branch
+    # that cannot be structured makes its target a leader, which may un-structure other branches.
+    order = sorted(instrs)
+    nxt_of = {a: a + instrs[a][5] for a in order}
+    structured = dict(fwd_branches)
+    changed = True
+    while changed:
+        changed = False
+        hard = set(leaders) | {t for pc, t in fwd_branches.items() if pc not in structured}
+        stack = []
+        for a in order:
+            while stack and stack[-1] <= a:
+                stack.pop()
+            if a in structured:
+                t = structured[a]
+                ok = not (stack and t > stack[-1])                 # proper nesting
+                b = nxt_of[a]
+                while ok and b < t:                                # contiguous, leader-free region
+                    if b not in instrs or b in hard:
+                        ok = False
+                        break
+                    b = nxt_of[b]
+                ok = ok and b == t and t in instrs
+                if not ok:
+                    del structured[a]
+                    changed = True
+                    break
+                stack.append(t)
+    leaders |= {t for pc, t in fwd_branches.items() if pc not in structured}
+    return instrs, leaders, structured
 
 
 def addr_class(a):
@@ -112,8 +149,10 @@ def addr_class(a):
 class Gen:
     def __init__(self, rom):
         self.rom = rom
-        self.instrs, self.leaders = traverse(rom)
+        self.instrs, self.leaders, self.structured = traverse(rom)
         self.out = []
+        self.goto_targets = set()
+        self.inline_backward = True
 
     def emit(self, s):
         self.out.append("    " + s)
@@ -199,7 +238,7 @@ class Gen:
         if static_ea is None:
             e(f"A26_WRITE_DYN(ea_, {val}, cyc + {cyc}u);")
             e(f"cyc += {cyc}u + stall_;")
-            e(f"if (done) {{ pc = 0x{nxt:04X}u; break; }}")
+            e(f"if (done) {{ pc = 0x{nxt:04X}u; goto a26_next_; }}")
             return False
         cls = addr_class(static_ea)
         if cls == "ram":
@@ -211,13 +250,25 @@ class Gen:
         else:
             reg = static_ea & 0x3F
             if reg == 0x02:                      # WSYNC: park until the end of the scanline, leave the block
-                e(f"cyc += {cyc}u; cyc += wsync_stall(cyc, cpu_ls); pc = 0x{nxt:04X}u; break;")
+                e(f"cyc += {cyc}u; cyc += wsync_stall(cyc, cpu_ls); pc = 0x{nxt:04X}u; goto a26_next_;")
                 return True
             e(f"if (!poke_quick(s, 0x{reg:02X}u, {val})) stall_ = tia_poke<VERIFY>(s, T, 0x{reg:02X}u, {val}, cyc + {cyc}u, cpu_ls, fb);")
             e(f"cyc += {cyc}u + stall_;")
             if reg == 0x00:
-                e(f"if (s.frame_done) {{ done = 1; pc = 0x{nxt:04X}u; break; }}")
+                e(f"if (s.frame_done) {{ done = 1; pc = 0x{nxt:04X}u; goto a26_next_; }}")
         return False
+
+    def is_intim_wait(self, pc, nxt):
+        if nxt not in self.instrs:
+            return False
+        mn, mode, cyc, b1, b2, n = self.instrs[nxt]
+        if mn != "BNE":
+            return False
+        t = (nxt + 2 + (b1 - 256 if b1 > 127 else b1)) & 0xFFFF
+        if t != pc:
+            return False
+        self.intim_taken = 3 + (1 if (t ^ (nxt + 2)) & 0xFF00 else 0)
+        return True
 
     def gen_instr(self, pc):
         mn, mode, cyc, b1, b2, n = self.instrs[pc]
@@ -225,7 +276,14 @@ class Gen:
         e = self.emit
         raw = " ".join("%02X" % rb(self.rom, pc + i) for i in range(n))
         self.out.append(f"  {{ /* {pc:04X}: {raw:<9}{mn} {mode} */")
+        self.cur_pc = pc
         ends = False
+        if mn == "LDA" and mode == "abs" and ((b1 | b2 << 8) & 0x1FFF) == 0x0284 and self.is_intim_wait(pc, nxt):
+            # `LDA INTIM; BNE *-3`: skip whole iterations that are known to read non-zero (exact: nothing but
+            # A, N, Z and the cycle counter changes in the loop, and the last iteration runs normally below)
+            period = 4 + self.intim_taken
+            e("{ const int32_t t0_ = s.timer_value - (int32_t)(cyc + 4u - s.timer_set); const int32_t unit_ = 1 << s.timer_shift;")
+            e(f"  if (s.timer_shift >= 3u && t0_ >= unit_) cyc += {period}u * ((uint32_t)(t0_ - unit_) / {period}u + 1u); }}")
         if mn in READ_OPS:
             self.read_operand(pc, mn, mode, cyc, b1, b2)
             if mn == "LDA": e("a = m; nv = zv = m;")
@@ -273,35 +331,45 @@ class Gen:
             flag, want = BRANCH[mn]
             t = (nxt + (b1 - 256 if b1 > 127 else b1)) & 0xFFFF
             taken = 3 + (1 if (t ^ nxt) & 0xFF00 else 0)
-            e(f"if ({flag} == {want}u) {{ pc = 0x{t:04X}u; cyc += {taken}u; break; }}")
+            if pc in self.structured:
+                e(f"if ({flag} == {want}u) {{ cyc += {taken}u; }} else {{ cyc += 2u;  /* structured: skips to {t:04X} */")
+                self.open_regions.append(t)
+                self.out.append("  /* region */")
+                return False
+            if t <= pc and t in self.leaders and self.inline_backward:
+                # backward branch: loop without a trip through the dispatcher
+                self.goto_targets.add(t)
+                e(f"if ({flag} == {want}u) {{ cyc += {taken}u; goto L_{t:04X}; }}")
+            else:
+                e(f"if ({flag} == {want}u) {{ pc = 0x{t:04X}u; cyc += {taken}u; goto a26_next_; }}")
             e("cyc += 2u;")
         elif mn == "JMP" and mode == "abs":
-            e(f"pc = 0x{b1 | b2 << 8:04X}u; cyc += 3u; break;")
+            e(f"pc = 0x{b1 | b2 << 8:04X}u; cyc += 3u; goto a26_next_;")
             ends = True
         elif mn == "JMP" and mode == "ind":
             p = b1 | b2 << 8
             p2 = (p & 0xFF00) | ((p + 1) & 0xFF)
             e(f"const uint32_t lo_ = bus_read<VERIFY>(s, T, ram, 0x{p & 0x1FFF:04X}u, cyc, 0x{b2:02X}u, fb), hi_ = bus_read<VERIFY>(s, T, ram, 0x{p2 & 0x1FFF:04X}u, cyc, lo_, fb);")
-            e("pc = lo_ | (hi_ << 8); cyc += 5u; break;")
+            e("pc = lo_ | (hi_ << 8); cyc += 5u; goto a26_next_;")
             ends = True
         elif mn == "JSR":
             ret = (pc + 2) & 0xFFFF
             e("uint32_t stall_ = 0;")
             e(f"A26_WRITE_DYN(0x100u | sp, 0x{ret >> 8:02X}u, cyc + 4u); sp = (sp - 1) & 0xFFu;")
             e(f"A26_WRITE_DYN(0x100u | sp, 0x{ret & 0xFF:02X}u, cyc + 5u); sp = (sp - 1) & 0xFFu;")
-            e(f"pc = 0x{b1 | b2 << 8:04X}u; cyc += 6u + stall_; break;")
+            e(f"pc = 0x{b1 | b2 << 8:04X}u; cyc += 6u + stall_; goto a26_next_;")
             ends = True
         elif mn == "RTS":
             e("sp = (sp + 1) & 0xFFu; const uint32_t lo_ = bus_read<VERIFY>(s, T, ram, 0x100u | sp, cyc, 0u, fb);")
             e("sp = (sp + 1) & 0xFFu; const uint32_t hi_ = bus_read<VERIFY>(s, T, ram, 0x100u | sp, cyc, lo_, fb);")
-            e("pc = ((lo_ | (hi_ << 8)) + 1) & 0xFFFFu; cyc += 6u; break;")
+            e("pc = ((lo_ | (hi_ << 8)) + 1) & 0xFFFFu; cyc += 6u; goto a26_next_;")
             ends = True
         elif mn == "RTI":
             e("sp = (sp + 1) & 0xFFu; const uint32_t p_ = bus_read<VERIFY>(s, T, ram, 0x100u | sp, cyc, 0u, fb);")
             e("A26_UNPACK_P(p_);")
             e("sp = (sp + 1) & 0xFFu; const uint32_t lo_ = bus_read<VERIFY>(s, T, ram, 0x100u | sp, cyc, p_, fb);")
             e("sp = (sp + 1) & 0xFFu; const uint32_t hi_ = bus_read<VERIFY>(s, T, ram, 0x100u | sp, cyc, lo_, fb);")
-            e("pc = lo_ | (hi_ << 8); cyc += 6u; break;")
+            e("pc = lo_ | (hi_ << 8); cyc += 6u; goto a26_next_;")
             ends = True
         elif mn == "BRK":
             ret = (pc + 2) & 0xFFFF
@@ -310,14 +378,14 @@ class Gen:
             e(f"A26_WRITE_DYN(0x100u | sp, 0x{ret >> 8:02X}u, cyc + 3u); sp = (sp - 1) & 0xFFu;")
             e(f"A26_WRITE_DYN(0x100u | sp, 0x{ret & 0xFF:02X}u, cyc + 4u); sp = (sp - 1) & 0xFFu;")
             e("A26_WRITE_DYN(0x100u | sp, p_, cyc + 5u); sp = (sp - 1) & 0xFFu;")
-            e(f"fid |= 4u; pc = 0x{vec:04X}u; cyc += 7u + stall_; break;")
+            e(f"fid |= 4u; pc = 0x{vec:04X}u; cyc += 7u + stall_; goto a26_next_;")
             ends = True
         elif mn in ("PHA", "PHP"):
             val = "a" if mn == "PHA" else "(A26_PACK_P() | 0x30u)"
             e(f"uint32_t stall_ = 0; const uint32_t v_ = {val};")
             e("A26_WRITE_DYN(0x100u | sp, v_, cyc + 3u); sp = (sp - 1) & 0xFFu;")
             e("cyc += 3u + stall_;")
-            e(f"if (done) {{ pc = 0x{nxt:04X}u; break; }}")
+            e(f"if (done) {{ pc = 0x{nxt:04X}u; goto a26_next_; }}")
         elif mn == "PLA":
             e("sp = (sp + 1) & 0xFFu; a = bus_read<VERIFY>(s, T, ram, 0x100u | sp, cyc + 4u, 0u, fb); nv = zv = a; cyc += 4u;")
         elif mn == "PLP":
@@ -352,9 +420,16 @@ class Gen:
         self.out.append("};")
         self.out.append("#else")
         prev_fell_through = False
+        self.open_regions = []
         for idx, pc in enumerate(order):
+            while self.open_regions and self.open_regions[-1] == pc:
+                self.open_regions.pop()
+                self.out.append("  } }  /* end of structured region */")
+                prev_fell_through = True          # the branch-taken path arrives here
             if pc in ids:
-                self.out.append(f"case {ids[pc]}:  /* ---- {pc:04X} ---- */")
+                if self.open_regions:
+                    raise SystemExit(f"leader {pc:04X} inside a structured region")
+                self.out.append(f"case {ids[pc]}: @LABEL_{pc:04X}@ /* ---- {pc:04X} ---- */")
             elif not prev_fell_through:
                 # unreachable by fall-through and not a leader: cannot happen (every entry is a leader)
                 raise SystemExit(f"instruction {pc:04X} is neither a leader nor reached by fall-through")
@@ -363,14 +438,22 @@ class Gen:
             if not ends:
                 if nxt not in self.instrs or (idx + 1 < len(order) and order[idx + 1] != nxt):
                     raise SystemExit(f"fall-through from {pc:04X} leaves the translated set")
+            elif self.open_regions and not (idx + 1 < len(order) and order[idx + 1] == self.open_regions[-1]):
+                # an unconditional transfer inside a structured region must be its last instruction
+                pass
             prev_fell_through = not ends
+        if self.open_regions:
+            raise SystemExit("unterminated structured region")
         self.out.append("#endif")
         os.makedirs(os.path.dirname(OUT_PATH), exist_ok=True)
+        text = "\n".join(self.out) + "\n"
+        text = re.sub(r"@LABEL_([0-9A-F]{4})@", lambda m: f"L_{m.group(1)}:" if int(m.group(1), 16) in self.goto_targets else "", text)
         with open(OUT_PATH, "w") as f:
-            f.write("\n".join(self.out) + "\n")
+            f.write(text)
         return len(order), len(leaders)
 
 
 if __name__ == "__main__":
-    n, l = Gen(load_rom()).generate()
-    print(f"wrote {os.path.relpath(OUT_PATH, ROOT)}: {n} instructions, {l} dispatch entries")
+    g = Gen(load_rom())
+    n, l = g.generate()
+    print(f"wrote {os.path.relpath(OUT_PATH, ROOT)}: {n} instructions, {l} dispatch entries, {len(g.structured)} structured branches")
