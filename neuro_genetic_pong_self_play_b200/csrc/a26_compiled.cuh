@@ -47,8 +47,12 @@ inline void fill_blockmap(uint16_t *dst) { for (int i = 0; i < 2048; ++i) dst[i]
         const uint32_t wa_ = (ADDR_) & 0x1FFFu;                                                       \
         if ((wa_ & 0x1280u) == 0x0080u) ram.wr(wa_, (VAL_));                                          \
         else if (!(wa_ & 0x1080u)) {                                                                  \
-            stall_ += tia_poke<VERIFY>(s, T, wa_ & 0x3Fu, (VAL_), (TAFTER_), cpu_ls, fb);             \
-            if (s.frame_done) done = 1;                                                               \
+            const uint32_t rg_ = wa_ & 0x3Fu;                                                         \
+            if (rg_ == 0x02u) stall_ += wsync_stall((TAFTER_), cpu_ls);                               \
+            else if (!poke_quick(s, rg_, (VAL_))) {                                                   \
+                stall_ += tia_poke<VERIFY>(s, T, rg_, (VAL_), (TAFTER_), cpu_ls, fb);                 \
+                if (s.frame_done) done = 1;                                                           \
+            }                                                                                         \
         } else if ((wa_ & 0x1280u) == 0x0280u) riot_poke(s, wa_, (VAL_), (TAFTER_));                  \
     } while (0)
 
@@ -66,7 +70,9 @@ __device__ __forceinline__ void run_frame_compiled(Chip &s, CpuRegs &r, const Ta
         const uint32_t line_end = cpu_ls + LINE_CYCLES;
         while ((int32_t)(cyc - line_end) < 0 && !done) {
             A26_STAT(5);
-            const uint32_t entry = (pc & 0x1000u) ? T.blockmap[pc & 0x7FFu] : 0u;
+            uint32_t entry;
+            A26_HOT_DISPATCH
+            entry = (pc & 0x1000u) ? T.blockmap[pc & 0x7FFu] : 0u;
             A26_STAT_ENTRY(pc);
             switch (entry) {
 #include "generated/pong_core.inc"

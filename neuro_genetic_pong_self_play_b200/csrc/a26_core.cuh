@@ -334,12 +334,14 @@ __device__ __forceinline__ bool quick_missile(QuickObj &o, uint32_t nusiz, uint3
     o.start = (int)pos; o.width = width; o.pat = (1u << width) - 1u; o.colour = colour;
     return true;
 }
-static __device__ __noinline__ bool render_span_quick(Chip &s, const Tables &T, int x0, int x1, int row)
+static __device__ __noinline__ bool render_span_quick(Chip &s, const Tables &T, int x0, int x1, int row_lo, int row_hi)
 {
     const uint32_t grp0 = (s.vdelp0 & 1) ? s.grp0_old : s.grp0_new, grp1 = (s.vdelp1 & 1) ? s.grp1_old : s.grp1_new;
     const bool bl_on = (((s.vdelbl & 1) ? s.enabl_old : s.enabl_new) & 2) != 0;
     const bool m0_on = (s.enam0 & 2) && !(s.resmp0 & 2), m1_on = (s.enam1 & 2) && !(s.resmp1 & 2);
-    const bool in_crop = row >= CROP_TOP && row < CROP_BOTTOM;
+    // rows [row_lo, row_hi) of the display window share this state; only those inside the crop count
+    const int clo = row_lo < CROP_TOP ? CROP_TOP : row_lo, chi = row_hi > CROP_BOTTOM ? CROP_BOTTOM : row_hi;
+    const bool in_crop = chi > clo;
     const bool pf_any = (s.pfmask[0] | s.pfmask[1] | s.pfmask[2] | s.pfmask[3] | s.pfmask[4]) != 0;
     const bool comb = s.hmove_blank && x0 < 8;
     if (!(grp0 | grp1) && !bl_on && !m0_on && !m1_on) {
@@ -372,7 +374,8 @@ static __device__ __noinline__ bool render_span_quick(Chip &s, const Tables &T, 
         for (int j = i + 1; j < 5; ++j)
             if (on[i] && on[j] && o[i].start < o[j].start + o[j].width && o[j].start < o[i].start + o[i].width) return false;
     if (!in_crop) return true;
-    const uint32_t cr = (uint32_t)(row - CROP_TOP);
+    const uint32_t nrows = (uint32_t)(chi - clo);
+    const uint32_t rowsum = nrows * (uint32_t)(clo - CROP_TOP) + nrows * (nrows - 1) / 2;   // sum of cropped row indices
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         if (!on[i]) continue;
@@ -388,7 +391,7 @@ static __device__ __noinline__ bool render_span_quick(Chip &s, const Tables &T, 
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
             const uint32_t w = (wts >> (2 * t)) & 3;
-            s.cnt[t] += w * n; s.sx[t] += w * sx; s.sy[t] += w * n * cr;
+            s.cnt[t] += w * n * nrows; s.sx[t] += w * sx * nrows; s.sy[t] += w * n * rowsum;
         }
     }
     return true;
@@ -503,7 +506,7 @@ __device__ __forceinline__ void render_to(Chip &s, const Tables &T, int x, uint8
     if (row >= 0 && row < FB_ROWS) {
         uint8_t *fb_row = (VERIFY && fb) ? fb + row * FB_COLS : nullptr;
         if (!(s.vblank & 2)) {
-            if (VERIFY || !render_span_quick(s, T, s.rx, x, row)) render_span<VERIFY>(s, T, s.rx, x, row, fb_row);
+            if (VERIFY || !render_span_quick(s, T, s.rx, x, row, row + 1)) render_span<VERIFY>(s, T, s.rx, x, row, fb_row);
         }
         // VBLANK: black; the framebuffer is pre-cleared to 0 and black matches no target channel
         // unless a target colour has a 0 channel, which accumulate_class would need to see:
@@ -517,14 +520,38 @@ __device__ __forceinline__ void render_to(Chip &s, const Tables &T, int x, uint8
     s.rx = x;
 }
 
+__device__ __forceinline__ void tia_newline(Chip &s, int k)
+{
+    s.line += k; s.tia_ls += (uint32_t)k * LINE_CYCLES; s.rx = 0; s.hmove_blank = 0; s.suppress = 0;
+}
+
+// k complete scanlines with the current register state, starting at the TIA's current (untouched) line.
+// In the fused mode they are accounted for in one step when the quick path applies.
+template <bool VERIFY>
+__device__ __forceinline__ void render_full_lines(Chip &s, const Tables &T, int k, uint8_t *fb)
+{
+    if (!VERIFY) {
+        const int row0 = s.line - YSTART;
+        const int lo = row0 < 0 ? 0 : row0, hi = row0 + k > FB_ROWS ? FB_ROWS : row0 + k;
+        bool handled;
+        if (hi <= lo) handled = true;                                   // outside the display window
+        else if (s.vblank & 2) handled = T.weight[0] == 0;              // black rows
+        else handled = render_span_quick(s, T, 0, FB_COLS, lo, hi);
+        if (handled) { tia_newline(s, k); return; }
+    }
+    for (int i = 0; i < k; ++i) { render_to<VERIFY>(s, T, FB_COLS, fb); tia_newline(s, 1); }
+}
+
 // bring the TIA up to colour clock h, measured from the start of its current scanline
 template <bool VERIFY>
 __device__ __forceinline__ void tia_catchup(Chip &s, const Tables &T, int h, uint8_t *fb)
 {
-    while (h > LINE_CLOCKS) {
-        render_to<VERIFY>(s, T, FB_COLS, fb);
-        s.line += 1; s.tia_ls += LINE_CYCLES; s.rx = 0; s.hmove_blank = 0; s.suppress = 0;
+    if (h > LINE_CLOCKS) {
+        render_to<VERIFY>(s, T, FB_COLS, fb);                           // finish the current line
+        tia_newline(s, 1);
         h -= LINE_CLOCKS;
+        const int full = (h - 1) / LINE_CLOCKS;                         // whole lines before the target line
+        if (full > 0) { render_full_lines<VERIFY>(s, T, full, fb); h -= full * LINE_CLOCKS; }
     }
     int x = h - HBLANK_CLOCKS;
     if (x > s.rx) render_to<VERIFY>(s, T, x > FB_COLS ? FB_COLS : x, fb);

@@ -30,6 +30,8 @@ BRANCH = {"BPL": ("((nv >> 7) & 1u)", 0), "BMI": ("((nv >> 7) & 1u)", 1), "BVC":
           "BEQ": ("(((zv & 0xFFu) == 0u) ? 1u : 0u)", 1)}
 PAGE_PENALTY = {"abx", "aby", "izy"}          # only for read instructions
 MAX_STRUCTURED_SKIP = 24                      # bytes a structured forward branch may skip
+# dispatch entries tried first, hottest first (dispatches per frame measured with tests/host_sim + A26_STATS)
+HOT_ENTRIES = [0xF621, 0xF58D, 0xF58B, 0xF5CC, 0xF5B8, 0xF21F, 0xF094]
 
 
 def load_rom():
@@ -446,6 +448,10 @@ class Gen:
             raise SystemExit("unterminated structured region")
         self.out.append("#endif")
         os.makedirs(os.path.dirname(OUT_PATH), exist_ok=True)
+        hot = [a for a in HOT_ENTRIES if a in ids]
+        self.goto_targets.update(hot)
+        chain = " ".join(f"if (pc == 0x{a:04X}u) goto L_{a:04X};" for a in hot)
+        self.out.insert(2, f"#define A26_HOT_DISPATCH {chain}")
         text = "\n".join(self.out) + "\n"
         text = re.sub(r"@LABEL_([0-9A-F]{4})@", lambda m: f"L_{m.group(1)}:" if int(m.group(1), 16) in self.goto_targets else "", text)
         with open(OUT_PATH, "w") as f:
