@@ -248,22 +248,24 @@ def main():
         except Exception:
             pass
         frames_rank0 = frames / world
-        inst_6507_per_s = frames_rank0 * FRAME_6507_INSTR / (rollout_ms * 1e-3) if rollout_ms > 0 else 0.0
-        warp_inst_per_6507 = prof.get("warp_inst_per_6507_inst")
-        issue_peak = sm_count * 4 * sm_mhz * 1e6                                  # warp-instructions/s the chip can issue
+        kernel_s = rollout_ms * 1e-3
+        inst_6507_per_s = frames_rank0 * FRAME_6507_INSTR / kernel_s if kernel_s > 0 else 0.0
+        tipf = prof.get("thread_inst_per_env_frame")
+        issue_peak = sm_count * 4 * 32 * sm_mhz * 1e6                             # thread-instructions/s the chip can issue
+        achieved = frames_rank0 * tipf / kernel_s if (tipf and kernel_s > 0) else None
+        hbm_alg = n * G * 4 + n * GAMES * 12 + n * 8                                # genomes in, rewards/frames/fitness out
         roofline = {
-            "bound": "issue (integer pipe; HBM traffic ~0 by design, tensor cores unused)",
-            "kernel": "rollout_kernel",
-            "achieved": (inst_6507_per_s * warp_inst_per_6507 / 32.0 / 1e9) if warp_inst_per_6507 else None,
-            "peak": issue_peak / 1e9, "unit": "G warp-inst/s",
-            "frac": (inst_6507_per_s * warp_inst_per_6507 / 32.0 / issue_peak) if warp_inst_per_6507 else None,
+            "bound": "issue",          # neither "hbm" nor "tensor" binds: per-env state is on-chip, no GEMM in the 6507/TIA core
+            "kernel": "rollout_kernel<1> (fused emulator + observation + policy + episode control)",
+            "achieved": achieved / 1e9 if achieved else None, "peak": issue_peak / 1e9, "unit": "G thread-inst/s",
+            "frac": achieved / issue_peak if achieved else None,
             "traffic": prof.get("dram_bytes_per_launch"),
-            "emulated_6507_inst_per_s": inst_6507_per_s,
+            "algorithmic_unit": "thread-instructions per env-frame at full lane convergence, from ncu: %s" % prof.get("source"),
+            "thread_inst_per_env_frame": tipf, "emulated_6507_inst_per_s": inst_6507_per_s,
             "kernel_ms_per_launch": rollout_ms / max(1, args.steps),
-            "hbm_algorithmic_bytes_per_launch": n * G * 4 + n * GAMES * 12 + n * 8,
-            "hbm_peak_gbs": peaks.get("hbm_gbs", 6650.0), "peak_source": "measured" if peaks else "fallback",
-            "note": "thread-per-environment 6507+TIA interpreter: state is on-chip, so HBM and tensor rooflines do not bind; "
-                    "achieved/frac use warp-instructions per emulated 6507 instruction from profiles/rollout_issue_model.json (ncu)",
+            "hbm": {"algorithmic_bytes_per_launch": hbm_alg, "achieved_gbs": hbm_alg * args.steps / kernel_s / 1e9 if kernel_s > 0 else None,
+                    "peak_gbs": peaks.get("hbm_gbs", 6650.0), "peak_source": "measured" if peaks else "fallback"},
+            "sm_clock_mhz_used": sm_mhz,
         }
         line = {
             "metric": "pong_selfplay_env_frames_per_sec_incl_nn_forward", "value": value, "unit": "env-frames/s", "n_gpus": world,
