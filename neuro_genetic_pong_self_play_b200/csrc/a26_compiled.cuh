@@ -46,14 +46,11 @@ inline void fill_blockmap(uint16_t *dst) { for (int i = 0; i < 2048; ++i) dst[i]
     do {                                                                                              \
         const uint32_t wa_ = (ADDR_) & 0x1FFFu;                                                       \
         if ((wa_ & 0x1280u) == 0x0080u) ram.wr(wa_, (VAL_));                                          \
-        else if (!(wa_ & 0x1080u)) {                                                                  \
-            const uint32_t rg_ = wa_ & 0x3Fu;                                                         \
-            if (rg_ == 0x02u) stall_ += wsync_stall((TAFTER_), cpu_ls);                               \
-            else if (!poke_quick(s, rg_, (VAL_))) {                                                   \
-                stall_ += tia_poke<VERIFY>(s, T, rg_, (VAL_), (TAFTER_), cpu_ls, fb);                 \
-                if (s.frame_done) done = 1;                                                           \
-            }                                                                                         \
-        } else if ((wa_ & 0x1280u) == 0x0280u) riot_poke(s, wa_, (VAL_), (TAFTER_));                  \
+        else if (!(wa_ & 0x1000u)) {                                                                  \
+            const uint32_t rs_ = io_write_slow<VERIFY>(s, T, wa_, (VAL_), (TAFTER_), cpu_ls, fb);     \
+            stall_ += rs_ & 0xFFFFu;                                                                  \
+            if (rs_ >> 16) done = 1;                                                                  \
+        }                                                                                             \
     } while (0)
 
 template <bool VERIFY>

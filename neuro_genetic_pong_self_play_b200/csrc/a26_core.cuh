@@ -565,38 +565,44 @@ __device__ __forceinline__ uint8_t wrap160(int v) { v %= 160; return (uint8_t)(v
 // true when the write has been fully handled here.
 __device__ __forceinline__ bool poke_quick(Chip &s, uint32_t reg, uint32_t v)
 {
+    // `same` = the bits of the register that can influence a pixel, a collision or an input are unchanged;
+    // the latch still takes the new byte (it is write-only, but the parity digest reads it back)
+#define A26_QUICK(FIELD, MASK) do { const bool same = ((v ^ s.FIELD) & (MASK)) == 0; if (same) s.FIELD = (uint8_t)v; return same; } while (0)
     switch (reg) {
     case 0x00: if (!((s.vsync & 2) && !(v & 2))) { s.vsync = (uint8_t)v; return true; } return false;
-    case 0x01: return v == s.vblank;
-    case 0x04: return v == s.nusiz0;
-    case 0x05: return v == s.nusiz1;
-    case 0x06: return v == s.colup0;
-    case 0x07: return v == s.colup1;
-    case 0x08: return v == s.colupf;
-    case 0x09: return v == s.colubk;
-    case 0x0A: return v == s.ctrlpf;
-    case 0x0B: return v == s.refp0;
-    case 0x0C: return v == s.refp1;
-    case 0x0D: return v == s.pf0;
+    case 0x01: A26_QUICK(vblank, 0x82);          // D1 blanking, D7 paddle dump
+    case 0x04: A26_QUICK(nusiz0, 0x37);
+    case 0x05: A26_QUICK(nusiz1, 0x37);
+    case 0x06: A26_QUICK(colup0, 0xFE);
+    case 0x07: A26_QUICK(colup1, 0xFE);
+    case 0x08: A26_QUICK(colupf, 0xFE);
+    case 0x09: A26_QUICK(colubk, 0xFE);
+    case 0x0A: A26_QUICK(ctrlpf, 0x37);
+    case 0x0B: A26_QUICK(refp0, 0x08);
+    case 0x0C: A26_QUICK(refp1, 0x08);
+    case 0x0D: A26_QUICK(pf0, 0xF0);
     case 0x0E: return v == s.pf1;
     case 0x0F: return v == s.pf2;
     case 0x1B: return v == s.grp0_new && s.grp1_old == s.grp1_new;
-    case 0x1C: return v == s.grp1_new && s.grp0_old == s.grp0_new && s.enabl_old == s.enabl_new;
-    case 0x1D: return v == s.enam0;
-    case 0x1E: return v == s.enam1;
-    case 0x1F: return v == s.enabl_new;
+    case 0x1C:
+        if (v == s.grp1_new && s.grp0_old == s.grp0_new && ((s.enabl_old ^ s.enabl_new) & 2) == 0) { s.enabl_old = s.enabl_new; return true; }
+        return false;
+    case 0x1D: A26_QUICK(enam0, 0x02);
+    case 0x1E: A26_QUICK(enam1, 0x02);
+    case 0x1F: A26_QUICK(enabl_new, 0x02);
     case 0x20: s.hmp0 = (uint8_t)v; return true;
     case 0x21: s.hmp1 = (uint8_t)v; return true;
     case 0x22: s.hmm0 = (uint8_t)v; return true;
     case 0x23: s.hmm1 = (uint8_t)v; return true;
     case 0x24: s.hmbl = (uint8_t)v; return true;
-    case 0x25: return v == s.vdelp0;
-    case 0x26: return v == s.vdelp1;
-    case 0x27: return v == s.vdelbl;
+    case 0x25: A26_QUICK(vdelp0, 0x01);
+    case 0x26: A26_QUICK(vdelp1, 0x01);
+    case 0x27: A26_QUICK(vdelbl, 0x01);
     case 0x2B: s.hmp0 = s.hmp1 = s.hmm0 = s.hmm1 = s.hmbl = 0; return true;
     case 0x03: case 0x15: case 0x16: case 0x17: case 0x18: case 0x19: case 0x1A: return true;
     default: return reg > 0x2C;
     }
+#undef A26_QUICK
 }
 
 // cycles the CPU parks after a WSYNC write that completed at cyc_after
@@ -771,15 +777,35 @@ __device__ __forceinline__ void clear_obs(Chip &s)
 }
 
 // ---- bus -----------------------------------------------------------------------------------------
+// device registers behind a run-time address (kept out of line: the inline expansion of every TIA/RIOT
+// path at every indexed access made the translated core several hundred KB of SASS)
+template <bool VERIFY>
+__device__ __noinline__ uint32_t io_read_slow(Chip &s, const Tables &T, uint32_t addr, uint32_t cyc_after, uint32_t dbus, uint8_t *fb)
+{
+    if (addr & 0x80) return riot_peek(s, addr, cyc_after);
+    return tia_peek<VERIFY>(s, T, addr, cyc_after, dbus, fb);
+}
+// returns stall cycles | (frame_done << 16)
+template <bool VERIFY>
+__device__ __noinline__ uint32_t io_write_slow(Chip &s, const Tables &T, uint32_t addr, uint32_t v, uint32_t cyc_after, uint32_t cpu_ls, uint8_t *fb)
+{
+    if (!(addr & 0x1080)) {
+        const uint32_t reg = addr & 0x3F;
+        if (reg == 0x02) return wsync_stall(cyc_after, cpu_ls);
+        if (poke_quick(s, reg, v)) return 0;
+        const uint32_t stall = tia_poke<VERIFY>(s, T, reg, v, cyc_after, cpu_ls, fb);
+        return stall | ((uint32_t)s.frame_done << 16);
+    }
+    if ((addr & 0x1280) == 0x0280) riot_poke(s, addr, v, cyc_after);
+    return 0;
+}
+
 template <bool VERIFY>
 __device__ __forceinline__ uint32_t bus_read(Chip &s, const Tables &T, Ram ram, uint32_t addr, uint32_t cyc_after, uint32_t dbus, uint8_t *fb)
 {
     if (addr & 0x1000) return rom_byte(T, addr);
-    if (addr & 0x80) {
-        if (!(addr & 0x200)) return ram.rd(addr);
-        return riot_peek(s, addr, cyc_after);
-    }
-    return tia_peek<VERIFY>(s, T, addr, cyc_after, dbus, fb);
+    if ((addr & 0x280) == 0x80) return ram.rd(addr);
+    return io_read_slow<VERIFY>(s, T, addr, cyc_after, dbus, fb);
 }
 
 // Run the 6507 until the frame ends (VSYNC turned off) -- one env.step of the reference.

@@ -7,6 +7,7 @@
 //   139-153, numpy_nn.NeuralNetwork.run 120-137, dumb_ais 1-25, utils.keep_within_game_bounds_please
 //   71-77, utils.calculate_reward 104-109, and gym-retro's env.reset/env.step underneath.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -381,12 +382,15 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
     int block = 32;
     long long warps = (total + 31) / 32;
     if (warps > (long long)h->sm_count * 16) block = 128;
+    // tuning overrides (experiments only)
+    if (const char *e = getenv("NGP_ROLLOUT_BLOCK")) { int b = atoi(e); if (b >= 32 && b <= 1024 && b % 32 == 0) block = b; }
     long long blocks = (total + block - 1) / block;
     const size_t smem = (size_t)block * 32 * 4;
     int per_sm = 0;
     auto kernel = p.core ? rollout_kernel<1> : rollout_kernel<0>;
     NGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
     if (per_sm < 1) per_sm = 1;
+    if (const char *e = getenv("NGP_ROLLOUT_BLOCKS_PER_SM")) { int b = atoi(e); if (b >= 1 && b < per_sm) per_sm = b; }
     const long long resident = (long long)per_sm * h->sm_count;
     if (blocks > resident) blocks = resident;            // persistent lanes pull the rest from the queue
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -159,6 +159,14 @@ class Gen:
     def emit(self, s):
         self.out.append("    " + s)
 
+    def zp_pointer(self, b1):
+        """the two pointer bytes of (zp),Y: straight RAM reads when both lie in console RAM"""
+        lo, hi = b1, (b1 + 1) & 0xFF
+        if lo >= 0x80 and hi >= 0x80:
+            return f"const uint32_t lo_ = ram.rd(0x{lo:02X}u), hi_ = ram.rd(0x{hi:02X}u);"
+        return (f"const uint32_t lo_ = bus_read<VERIFY>(s, T, ram, 0x{lo:02X}u, cyc, 0x{b1:02X}u, fb), "
+                f"hi_ = bus_read<VERIFY>(s, T, ram, 0x{hi:02X}u, cyc, lo_, fb);")
+
     # -- operand fetch for read instructions: returns expression for the byte, sets cycle expression
     def read_operand(self, pc, mn, mode, cyc, b1, b2):
         """emit code defining `m` (uint32_t) and `n_` (cycles); returns nothing"""
@@ -195,7 +203,7 @@ class Gen:
                 e(f"const uint32_t m = bus_read<VERIFY>(s, T, ram, ea_ & 0x1FFFu, cyc + n_, 0x{b2:02X}u, fb);")
             return
         if mode == "izy":
-            e(f"const uint32_t lo_ = bus_read<VERIFY>(s, T, ram, 0x{b1:02X}u, cyc, 0x{b1:02X}u, fb), hi_ = bus_read<VERIFY>(s, T, ram, 0x{(b1 + 1) & 0xFF:02X}u, cyc, lo_, fb);")
+            e(self.zp_pointer(b1))
             e("const uint32_t base_ = lo_ | (hi_ << 8), ea_ = (base_ + y) & 0xFFFFu;")
             e(f"const uint32_t n_ = {cyc}u + (((base_ & 0xFFu) + y) >> 8);")
             e("const uint32_t m = bus_read<VERIFY>(s, T, ram, ea_ & 0x1FFFu, cyc + n_, hi_, fb);")
@@ -224,7 +232,7 @@ class Gen:
             e(f"const uint32_t ea_ = (0x{b1 | b2 << 8:04X}u + {r}) & 0x1FFFu;")
             return None
         if mode == "izy":
-            e(f"const uint32_t lo_ = bus_read<VERIFY>(s, T, ram, 0x{b1:02X}u, cyc, 0x{b1:02X}u, fb), hi_ = bus_read<VERIFY>(s, T, ram, 0x{(b1 + 1) & 0xFF:02X}u, cyc, lo_, fb);")
+            e(self.zp_pointer(b1))
             e("const uint32_t ea_ = ((lo_ | (hi_ << 8)) + y) & 0x1FFFu;")
             return None
         if mode == "izx":
