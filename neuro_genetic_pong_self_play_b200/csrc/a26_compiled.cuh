@@ -47,41 +47,64 @@ inline void fill_blockmap(uint16_t *dst) { for (int i = 0; i < 2048; ++i) dst[i]
         const uint32_t wa_ = (ADDR_) & 0x1FFFu;                                                       \
         if ((wa_ & 0x1280u) == 0x0080u) ram.wr(wa_, (VAL_));                                          \
         else if (!(wa_ & 0x1000u)) {                                                                  \
-            const uint32_t rs_ = io_write_slow<VERIFY>(s, T, wa_, (VAL_), (TAFTER_), cpu_ls, fb);     \
+            const uint32_t rs_ = io_write_slow<VERIFY, true>(s, T, wa_, (VAL_), (TAFTER_), cpu_ls, fb);     \
             stall_ += rs_ & 0xFFFFu;                                                                  \
             if (rs_ >> 16) done = 1;                                                                  \
         }                                                                                             \
     } while (0)
 
-template <bool VERIFY>
-__device__ __forceinline__ void run_frame_compiled(Chip &s, CpuRegs &r, const Tables &T, Ram ram, uint8_t *fb)
+// scanline slots a regular NTSC frame touches (262 lines; a frame starts and ends a few cycles into a line)
+constexpr uint32_t SYNC_SLOTS = 263;
+
+// SYNC: every thread of the CTA (active or not) makes one barrier call per scanline slot, so that all warps
+// of the CTA walk through the frame together.  Warps that drift apart execute different parts of the
+// ~250 KB of translated code and evict each other from the 32 KB instruction cache (measured: 21 stall
+// cycles per issued instruction in a saturated launch without this); in step, one miss serves all warps.
+template <bool VERIFY, bool SYNC>
+__device__ __forceinline__ void run_frame_compiled(Chip &s, CpuRegs &r, const Tables &T, Ram ram, uint8_t *fb, bool active = true)
 {
-    uint32_t a = r.a, x = r.x, y = r.y, sp = r.sp, pc = r.pc;
-    uint32_t fc = r.c, fv = r.v, nv = r.nv, zv = r.zv, fid = r.id;
-    uint32_t cyc = r.cyc, cpu_ls = r.cpu_ls;
-    const uint32_t start_cyc = cyc;
-    uint32_t done = 0;
-    s.frame_done = 0;
-    if (s.error) done = 1;
-    while (!done && (cyc - start_cyc) < FRAME_CYCLE_CAP) {
-        const uint32_t line_end = cpu_ls + LINE_CYCLES;
-        while ((int32_t)(cyc - line_end) < 0 && !done) {
-            A26_STAT(5);
-            uint32_t entry;
-            A26_HOT_DISPATCH
-            entry = (pc & 0x1000u) ? T.blockmap[pc & 0x7FFu] : 0u;
-            A26_STAT_ENTRY(pc);
-            switch (entry) {
-#include "generated/pong_core.inc"
-            default:
-                s.error = (uint8_t)((pc & 0x1000u) ? (int)ERR_UNTRANSLATED : (int)ERR_PC_NOT_ROM);
-                done = 1;
-                break;
-            }
-        a26_next_:;
-        }
-        while ((int32_t)(cyc - (cpu_ls + LINE_CYCLES)) >= 0) cpu_ls += LINE_CYCLES;
+    uint32_t a = 0, x = 0, y = 0, sp = 0, pc = 0, fc = 0, fv = 0, nv = 0, zv = 0, fid = 0, cyc = 0, cpu_ls = 0;
+    uint32_t done = 1;
+    if (active) {
+        a = r.a; x = r.x; y = r.y; sp = r.sp; pc = r.pc;
+        fc = r.c; fv = r.v; nv = r.nv; zv = r.zv; fid = r.id;
+        cyc = r.cyc; cpu_ls = r.cpu_ls;
+        s.frame_done = 0;
+        done = s.error ? 1 : 0;
     }
+    const uint32_t start_cyc = cyc;
+    for (uint32_t slot = 0;; ++slot) {
+        if (!done) {
+            if ((cyc - start_cyc) >= FRAME_CYCLE_CAP) done = 1;
+            else {
+                const uint32_t line_end = cpu_ls + LINE_CYCLES;
+                while ((int32_t)(cyc - line_end) < 0 && !done) {
+                    A26_STAT(5);
+                    uint32_t entry;
+                    A26_HOT_DISPATCH
+                    entry = (pc & 0x1000u) ? T.blockmap[pc & 0x7FFu] : 0u;
+                    A26_STAT_ENTRY(pc);
+                    switch (entry) {
+#include "generated/pong_core.inc"
+                    default:
+                        s.error = (uint8_t)((pc & 0x1000u) ? (int)ERR_UNTRANSLATED : (int)ERR_PC_NOT_ROM);
+                        done = 1;
+                        break;
+                    }
+                a26_next_:;
+                }
+                // scanline boundary: the warp is converged here; replay the latch writes queued during the line
+                if (s.nlog) tia_flush<VERIFY>(s, T, fb);
+                while ((int32_t)(cyc - (cpu_ls + LINE_CYCLES)) >= 0) cpu_ls += LINE_CYCLES;
+            }
+        }
+        if (SYNC) {
+            if (slot + 1 < SYNC_SLOTS) __syncthreads();
+            else if (!__syncthreads_or(!done)) break;
+        } else if (done) break;
+    }
+    if (!active) return;
+    if (s.nlog) tia_flush<VERIFY>(s, T, fb);
     tia_catchup<VERIFY>(s, T, 3 * (int)(cyc - s.tia_ls), fb);
     r.a = a; r.x = x; r.y = y; r.sp = sp; r.pc = pc; r.c = fc; r.v = fv; r.nv = nv; r.zv = zv; r.id = fid;
     r.cyc = cyc; r.cpu_ls = cpu_ls;

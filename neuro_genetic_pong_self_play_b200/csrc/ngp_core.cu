@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(32) env_step_kernel(const Tables *tables, cons
     a26::apply_input(s, needed, 0x3F, fire, dec, inc);
     a26::clear_obs(s);
     uint8_t *my_fb = fb ? fb + (size_t)e * a26::FB_ROWS * a26::FB_COLS : nullptr;
-    if (core) a26::run_frame_compiled<true>(s, r, T, ram, my_fb);
+    if (core) a26::run_frame_compiled<true, false>(s, r, T, ram, my_fb);
     else a26::run_frame<true>(s, r, T, ram, my_fb);
     store_snapshot(&envs[e], s, r, ram);
     if (s.error) atomicAdd(&counters[2], 1ull);
@@ -166,7 +166,7 @@ __global__ void env_digest_kernel(const Snapshot *envs, int n, uint32_t *out)
 // Fused rollout: one environment (= one game of one genome) per thread.  Lanes are persistent and
 // pull the next environment from a global counter at frame boundaries, so a warp stays in
 // scanline lock-step whatever episode each of its lanes is in.
-template <int CORE>
+template <int CORE, bool SYNC>
 __global__ void rollout_kernel(RolloutParams p)
 {
     __shared__ Tables T;
@@ -186,11 +186,14 @@ __global__ void rollout_kernel(RolloutParams p)
             if (e < total) roll::episode_begin(ep, p, e, s, r, ram);
             else exhausted = true;
         }
-        if (__all_sync(0xFFFFFFFFu, ep.env < 0)) break;
-        if (ep.env >= 0) {
+        const bool active = ep.env >= 0;
+        // SYNC: the CTA walks through frames together (CTA-wide barriers inside the frame), so it also stops together
+        if (SYNC) { if (!__syncthreads_or(active)) break; }
+        else if (__all_sync(0xFFFFFFFFu, !active)) break;
+        if (SYNC || active) {
             double reward;
-            const bool done = roll::episode_frame<CORE>(ep, p, s, r, T, ram, &reward);
-            my_frames++;
+            const bool done = roll::episode_frame<CORE, SYNC>(ep, p, s, r, T, ram, &reward, active);
+            if (active) my_frames++;
             if (done) {
                 p.rewards[ep.env] = reward;
                 p.frames[ep.env] = ep.frame;
@@ -381,13 +384,14 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
     // all SM sub-partitions), larger CTAs in multiples of the SM count once they do
     int block = 32;
     long long warps = (total + 31) / 32;
-    if (warps > (long long)h->sm_count * 16) block = 128;
+    if (warps > (long long)h->sm_count * 16) block = p.core ? 256 : 128;   // CTA-synchronous mode: bigger CTAs share instruction fetches
     // tuning overrides (experiments only)
     if (const char *e = getenv("NGP_ROLLOUT_BLOCK")) { int b = atoi(e); if (b >= 32 && b <= 1024 && b % 32 == 0) block = b; }
+    const bool sync = p.core && block > 32 && !getenv("NGP_ROLLOUT_NOSYNC");
+    auto kernel = !p.core ? rollout_kernel<0, false> : (sync ? rollout_kernel<1, true> : rollout_kernel<1, false>);
     long long blocks = (total + block - 1) / block;
     const size_t smem = (size_t)block * 32 * 4;
     int per_sm = 0;
-    auto kernel = p.core ? rollout_kernel<1> : rollout_kernel<0>;
     NGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
     if (per_sm < 1) per_sm = 1;
     if (const char *e = getenv("NGP_ROLLOUT_BLOCKS_PER_SM")) { int b = atoi(e); if (b >= 1 && b < per_sm) per_sm = b; }

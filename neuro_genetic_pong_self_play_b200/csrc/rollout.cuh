@@ -153,16 +153,21 @@ __device__ __forceinline__ void episode_begin(Episode &ep, const RolloutParams &
 
 // One iteration of perform_episode's loop (main.py:76-107).  Returns true when the episode ended;
 // then *reward holds main.py:109-112's value.
-template <int CORE>
+// `active` = this lane owns an environment; with SYNC every thread of the CTA must come through here (the
+// frame contains CTA-wide barriers), inactive lanes only take part in the barriers.
+template <int CORE, bool SYNC = false>
 __device__ __forceinline__ bool episode_frame(Episode &ep, const RolloutParams &p, Chip &s, CpuRegs &r, const Tables &T, Ram ram,
-                                              double *reward)
+                                              double *reward, bool active = true)
 {
-    uint32_t fire, dec, inc;
-    acts_to_input(ep.left_act, ep.right_act, fire, dec, inc);
-    a26::apply_input(s, p.needed, 0x3F, fire, dec, inc);
-    a26::clear_obs(s);
-    if (CORE) a26::run_frame_compiled<false>(s, r, T, ram, nullptr);
-    else a26::run_frame<false>(s, r, T, ram, nullptr);
+    if (active) {
+        uint32_t fire, dec, inc;
+        acts_to_input(ep.left_act, ep.right_act, fire, dec, inc);
+        a26::apply_input(s, p.needed, 0x3F, fire, dec, inc);
+        a26::clear_obs(s);
+    }
+    if (CORE) a26::run_frame_compiled<false, SYNC>(s, r, T, ram, nullptr, active);
+    else if (active) a26::run_frame<false>(s, r, T, ram, nullptr);
+    if (!active) return false;
     const int s1 = (int)ram.rd(13), s2 = (int)ram.rd(14);          // score1 = $8D, score2 = $8E
     // ---- observation (find_stuff) ----
     bool valid[3]; double loc[3][2];

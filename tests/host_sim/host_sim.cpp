@@ -35,6 +35,8 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline void __syncthreads() {}
+static inline int __syncthreads_or(int v) { return v; }
 
 #include "../../neuro_genetic_pong_self_play_b200/csrc/rollout.cuh"
 #include "../../neuro_genetic_pong_self_play_b200/csrc/host_tables.h"
@@ -105,7 +107,7 @@ int hs_env_run_frame(void *h, int core, int swchb, int fire, int dec, int inc, u
     a26::apply_input(s, sim->needed.data(), (uint32_t)swchb, (uint32_t)fire, (uint32_t)dec, (uint32_t)inc);
     a26::clear_obs(s);
     if (fb) memset(fb, 0, 210 * 160);
-    if (core) a26::run_frame_compiled<true>(s, sim->r, sim->T, ram, fb);
+    if (core) a26::run_frame_compiled<true, false>(s, sim->r, sim->T, ram, fb);
     else a26::run_frame<true>(s, sim->r, sim->T, ram, fb);
     if (ram_out) for (int i = 0; i < 128; ++i) ram_out[i] = (uint8_t)ram.rd(i);
     if (loc && valid)
@@ -142,7 +144,7 @@ int hs_env_step_fast(void *h, int core, const uint8_t *action16, uint8_t *ram_ou
     roll::action_to_input(action16, fire, dec, inc);
     a26::apply_input(s, sim->needed.data(), 0x3F, fire, dec, inc);
     a26::clear_obs(s);
-    if (core) a26::run_frame_compiled<false>(s, sim->r, sim->T, ram, nullptr);
+    if (core) a26::run_frame_compiled<false, false>(s, sim->r, sim->T, ram, nullptr);
     else a26::run_frame<false>(s, sim->r, sim->T, ram, nullptr);
     for (int i = 0; i < 128; ++i) ram_out[i] = (uint8_t)ram.rd(i);
     for (int t = 0; t < 3; ++t) {

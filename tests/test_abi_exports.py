@@ -60,3 +60,13 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
                 assert "oracle/" not in text or f == "build.py", f
+
+
+def test_generated_core_is_up_to_date(tmp_path):
+    """csrc/generated/pong_core.inc is exactly what tools/gen_rom_core.py emits for the bundled cartridge."""
+    import subprocess
+    import sys
+    out = tmp_path / "pong_core.inc"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_rom_core.py"), str(out)])
+    committed = open(os.path.join(ROOT, "neuro_genetic_pong_self_play_b200", "csrc", "generated", "pong_core.inc")).read()
+    assert out.read_text() == committed

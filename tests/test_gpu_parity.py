@@ -171,6 +171,14 @@ def test_evaluate_population_1024_properties(ngp):
     a = eng.evaluate(genomes, seed=1, want_detail=True)
     b = eng.evaluate(genomes, seed=1, want_detail=True)
     assert torch.equal(a["fitness"], b["fitness"]) and torch.equal(a["frames"], b["frames"])
+    # CTA-synchronous launch geometry (what large populations use) gives the same bits
+    for blk in ("128", "256"):
+        os.environ["NGP_ROLLOUT_BLOCK"] = blk
+        try:
+            c = eng.evaluate(genomes, seed=1, want_detail=True)
+        finally:
+            del os.environ["NGP_ROLLOUT_BLOCK"]
+        assert torch.equal(a["fitness"], c["fitness"]) and torch.equal(a["frames"], c["frames"]) and torch.equal(a["rewards"], c["rewards"])
     fit_h, total_h = eng.evaluate_host(genomes.cpu().numpy(), seed=1)
     assert np.array_equal(fit_h, a["fitness"].cpu().numpy()) and total_h == a["frames_total"]
     frames = a["frames"].cpu().numpy()

@@ -25,6 +25,9 @@ def main():
     rep = sys.argv[1]
     kernel = sys.argv[2] if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else "rollout_kernel"
     top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 40
+    global CSRC
+    if "--src" in sys.argv:      # csrc directory of the profiled source (e.g. from `git archive <commit>`)
+        CSRC = sys.argv[sys.argv.index("--src") + 1]
     tmp = tempfile.mkdtemp()
     cubin = os.path.join(tmp, "core.cubin")
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-cubin", "-o", cubin,
