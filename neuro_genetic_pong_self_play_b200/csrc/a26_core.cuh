@@ -146,6 +146,7 @@ struct Chip {
     uint32_t cnt[3], sx[3], sy[3];
     // deferred register writes of the current scanline (translated core): time and reg | val<<8 | cycle-in-line<<16
     uint32_t log_t[LOG_CAP], log_e[LOG_CAP];
+    uint32_t log_mask[2];    // bit per TIA register (0x00..0x3F) that has a queued write
 };
 
 // CPU-visible part of an environment that is not in Chip
@@ -707,6 +708,7 @@ __device__ __noinline__ void tia_flush(Chip &s, const Tables &T, uint8_t *fb)
         tia_apply<VERIFY>(s, T, e & 0xFF, (e >> 8) & 0xFF, s.log_t[i], (e >> 16) & 0xFF, fb);
     }
     s.nlog = 0;
+    s.log_mask[0] = s.log_mask[1] = 0;
 }
 
 // TIA register write, immediate.  cyc_after = CPU cycle count after the write cycle; cpu_ls = a CPU cycle at
@@ -728,6 +730,19 @@ __device__ __forceinline__ bool is_level_reg(uint32_t reg)
     return (reg >= 0x04 && reg <= 0x0F) || (reg >= 0x1B && reg <= 0x1F) || (reg >= 0x25 && reg <= 0x27);
 }
 
+// With writes queued, the latches lag behind the CPU's view only for the registers that have a queued
+// write (GRP0, GRP1 and ENABL latch each other, so they are treated as one group).  For every other
+// register the "nothing visible changes" test against the latch is still exact.
+__device__ __forceinline__ bool poke_quick_pending(Chip &s, uint32_t reg, uint32_t v)
+{
+    if (s.nlog) {
+        const uint32_t grp = (1u << 0x1B) | (1u << 0x1C) | (1u << 0x1F);
+        const uint32_t dep = (reg == 0x1B || reg == 0x1C || reg == 0x1F) ? grp : (1u << (reg & 31));
+        if (s.log_mask[reg >> 5] & dep) return false;
+    }
+    return poke_quick(s, reg, v);
+}
+
 // TIA register write of the translated core: a latch change is queued and replayed at the next scanline
 // boundary, where the whole warp is converged (the replay = catch-up rendering is the expensive, rarely
 // taken path; executing it once per scanline for all lanes instead of once per lane-event is what keeps
@@ -736,11 +751,12 @@ template <bool VERIFY>
 __device__ __noinline__ uint32_t tia_poke_deferred(Chip &s, const Tables &T, uint32_t reg, uint32_t v, uint32_t cyc_after, uint32_t cpu_ls, uint8_t *fb)
 {
     if (!is_level_reg(reg)) return tia_poke<VERIFY>(s, T, reg, v, cyc_after, cpu_ls, fb);
-    if (s.nlog == 0 && poke_quick(s, reg, v)) return 0;
+    if (poke_quick_pending(s, reg, v)) return 0;
     int n = s.nlog;
     if (n == LOG_CAP) { tia_flush<VERIFY>(s, T, fb); n = 0; }
     s.log_t[n] = cyc_after;
     s.log_e[n] = reg | ((v & 0xFF) << 8) | (((cyc_after - cpu_ls) % LINE_CYCLES) << 16);
+    s.log_mask[reg >> 5] |= 1u << (reg & 31);
     s.nlog = (uint8_t)(n + 1);
     return 0;
 }

@@ -264,7 +264,7 @@ class Gen:
                 return True
             level = (0x04 <= reg <= 0x0F) or (0x1B <= reg <= 0x1F) or (0x25 <= reg <= 0x27)
             if level:   # latch write: queued until the scanline boundary unless provably invisible
-                e(f"if (s.nlog || !poke_quick(s, 0x{reg:02X}u, {val})) tia_poke_deferred<VERIFY>(s, T, 0x{reg:02X}u, {val}, cyc + {cyc}u, cpu_ls, fb);")
+                e(f"if (!poke_quick_pending(s, 0x{reg:02X}u, {val})) tia_poke_deferred<VERIFY>(s, T, 0x{reg:02X}u, {val}, cyc + {cyc}u, cpu_ls, fb);")
             else:
                 e(f"if (s.nlog || !poke_quick(s, 0x{reg:02X}u, {val})) stall_ = tia_poke<VERIFY>(s, T, 0x{reg:02X}u, {val}, cyc + {cyc}u, cpu_ls, fb);")
             e(f"cyc += {cyc}u + stall_;")
