@@ -855,7 +855,7 @@ __device__ __noinline__ uint32_t io_write_slow(Chip &s, const Tables &T, uint32_
         const uint32_t reg = addr & 0x3F;
         if (reg == 0x02) return wsync_stall(cyc_after, cpu_ls);
         if (DEFER) return tia_poke_deferred<VERIFY>(s, T, reg, v, cyc_after, cpu_ls, fb) | ((uint32_t)s.frame_done << 16);
-        if (s.nlog == 0 && poke_quick(s, reg, v)) return 0;
+        if (poke_quick(s, reg, v)) return 0;
         const uint32_t stall = tia_poke<VERIFY>(s, T, reg, v, cyc_after, cpu_ls, fb);
         return stall | ((uint32_t)s.frame_done << 16);
     }
