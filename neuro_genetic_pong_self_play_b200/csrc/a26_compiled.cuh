@@ -47,7 +47,7 @@ inline void fill_blockmap(uint16_t *dst) { for (int i = 0; i < 2048; ++i) dst[i]
         const uint32_t wa_ = (ADDR_) & 0x1FFFu;                                                       \
         if ((wa_ & 0x1280u) == 0x0080u) ram.wr(wa_, (VAL_));                                          \
         else if (!(wa_ & 0x1000u)) {                                                                  \
-            const uint32_t rs_ = io_write_slow<VERIFY, DEFER>(s, T, wa_, (VAL_), (TAFTER_), cpu_ls, fb);     \
+            const uint32_t rs_ = io_write_slow<VERIFY>(s, T, wa_, (VAL_), (TAFTER_), cpu_ls, fb);     \
             stall_ += rs_ & 0xFFFFu;                                                                  \
             if (rs_ >> 16) done = 1;                                                                  \
         }                                                                                             \
@@ -60,7 +60,7 @@ constexpr uint32_t SYNC_SLOTS = 263;
 // of the CTA walk through the frame together.  Warps that drift apart execute different parts of the
 // ~250 KB of translated code and evict each other from the 32 KB instruction cache (measured: 21 stall
 // cycles per issued instruction in a saturated launch without this); in step, one miss serves all warps.
-template <bool VERIFY, bool SYNC, bool DEFER = false>
+template <bool VERIFY, bool SYNC>
 __device__ __forceinline__ void run_frame_compiled(Chip &s, CpuRegs &r, const Tables &T, Ram ram, uint8_t *fb, bool active = true)
 {
     uint32_t a = 0, x = 0, y = 0, sp = 0, pc = 0, fc = 0, fv = 0, nv = 0, zv = 0, fid = 0, cyc = 0, cpu_ls = 0;
@@ -93,8 +93,6 @@ __device__ __forceinline__ void run_frame_compiled(Chip &s, CpuRegs &r, const Ta
                     }
                 a26_next_:;
                 }
-                // scanline boundary: the warp is converged here; replay the latch writes queued during the line
-                if (s.nlog) tia_flush<VERIFY>(s, T, fb);
                 while ((int32_t)(cyc - (cpu_ls + LINE_CYCLES)) >= 0) cpu_ls += LINE_CYCLES;
             }
         }
@@ -104,7 +102,6 @@ __device__ __forceinline__ void run_frame_compiled(Chip &s, CpuRegs &r, const Ta
         } else if (done) break;
     }
     if (!active) return;
-    if (s.nlog) tia_flush<VERIFY>(s, T, fb);
     tia_catchup<VERIFY>(s, T, 3 * (int)(cyc - s.tia_ls), fb);
     r.a = a; r.x = x; r.y = y; r.sp = sp; r.pc = pc; r.c = fc; r.v = fv; r.nv = nv; r.zv = zv; r.id = fid;
     r.cyc = cyc; r.cpu_ls = cpu_ls;

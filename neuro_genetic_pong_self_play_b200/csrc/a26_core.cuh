@@ -44,7 +44,6 @@ constexpr int TRIGMAX = 4096;
 constexpr int PADDLE_DIGITAL_SENSITIVITY = 5;
 constexpr int PADDLE_DIGITAL_DISTANCE = 60;
 constexpr uint32_t FRAME_CYCLE_CAP = 4 * 262 * 76;
-constexpr int LOG_CAP = 6;       // deferred TIA writes kept per environment before a forced flush
 
 enum : int { ERR_NONE = 0, ERR_ILLEGAL_OPCODE = 1, ERR_DECIMAL = 2, ERR_PC_NOT_ROM = 3 };
 
@@ -127,7 +126,7 @@ struct Chip {
     uint8_t grp1_new, grp1_old, enam0, enam1, enabl_new, enabl_old, hmp0, hmp1;
     uint8_t hmm0, hmm1, hmbl, vdelp0, vdelp1, vdelbl, resmp0, resmp1;
     uint8_t posp0, posp1, posm0, posm1, posbl, suppress, hmove_blank, frame_done;
-    uint8_t swcha, swchb, dump_enabled, keyrep, error, nlog, pad1, pad2;   // nlog: pending deferred writes
+    uint8_t swcha, swchb, dump_enabled, keyrep, error, pad0, pad1, pad2;
     uint16_t cx, pad3;
     // renderer
     int32_t line;            // TIA scanline relative to the frame start
@@ -144,9 +143,6 @@ struct Chip {
     uint32_t needed[4];
     // observation accumulators (reference find_stuff, utils.py:14-19,60-68)
     uint32_t cnt[3], sx[3], sy[3];
-    // deferred register writes of the current scanline (translated core): time and reg | val<<8 | cycle-in-line<<16
-    uint32_t log_t[LOG_CAP], log_e[LOG_CAP];
-    uint32_t log_mask[2];    // bit per TIA register (0x00..0x3F) that has a queued write
 };
 
 // CPU-visible part of an environment that is not in Chip
@@ -698,66 +694,15 @@ __device__ __forceinline__ void tia_apply(Chip &s, const Tables &T, uint32_t reg
     }
 }
 
-// replay the deferred writes in order
-template <bool VERIFY>
-__device__ __noinline__ void tia_flush(Chip &s, const Tables &T, uint8_t *fb)
-{
-    const int n = s.nlog;
-    for (int i = 0; i < n; ++i) {
-        const uint32_t e = s.log_e[i];
-        tia_apply<VERIFY>(s, T, e & 0xFF, (e >> 8) & 0xFF, s.log_t[i], (e >> 16) & 0xFF, fb);
-    }
-    s.nlog = 0;
-    s.log_mask[0] = s.log_mask[1] = 0;
-}
-
-// TIA register write, immediate.  cyc_after = CPU cycle count after the write cycle; cpu_ls = a CPU cycle at
+// TIA register write.  cyc_after = CPU cycle count after the write cycle; cpu_ls = a CPU cycle at
 // which some scanline started.  Returns the number of cycles the CPU stalls (WSYNC).
 template <bool VERIFY>
 __device__ __noinline__ uint32_t tia_poke(Chip &s, const Tables &T, uint32_t reg, uint32_t v, uint32_t cyc_after, uint32_t cpu_ls, uint8_t *fb)
 {
     A26_STAT(0);
     if (reg == 0x02) return wsync_stall(cyc_after, cpu_ls);
-    if (s.nlog) tia_flush<VERIFY>(s, T, fb);
     if (poke_quick(s, reg, v)) return 0;
     tia_apply<VERIFY>(s, T, reg, v, cyc_after, (cyc_after - cpu_ls) % LINE_CYCLES, fb);
-    return 0;
-}
-
-// registers whose writes may wait for the end of the scanline (pure latches; no strobe, no input side)
-__device__ __forceinline__ bool is_level_reg(uint32_t reg)
-{
-    return (reg >= 0x04 && reg <= 0x0F) || (reg >= 0x1B && reg <= 0x1F) || (reg >= 0x25 && reg <= 0x27);
-}
-
-// With writes queued, the latches lag behind the CPU's view only for the registers that have a queued
-// write (GRP0, GRP1 and ENABL latch each other, so they are treated as one group).  For every other
-// register the "nothing visible changes" test against the latch is still exact.
-__device__ __forceinline__ bool poke_quick_pending(Chip &s, uint32_t reg, uint32_t v)
-{
-    if (s.nlog) {
-        const uint32_t grp = (1u << 0x1B) | (1u << 0x1C) | (1u << 0x1F);
-        const uint32_t dep = (reg == 0x1B || reg == 0x1C || reg == 0x1F) ? grp : (1u << (reg & 31));
-        if (s.log_mask[reg >> 5] & dep) return false;
-    }
-    return poke_quick(s, reg, v);
-}
-
-// TIA register write of the translated core: a latch change is queued and replayed at the next scanline
-// boundary, where the whole warp is converged (the replay = catch-up rendering is the expensive, rarely
-// taken path; executing it once per scanline for all lanes instead of once per lane-event is what keeps
-// diverged warps efficient).  Strobes and input-related registers flush the queue and apply at once.
-template <bool VERIFY>
-__device__ __noinline__ uint32_t tia_poke_deferred(Chip &s, const Tables &T, uint32_t reg, uint32_t v, uint32_t cyc_after, uint32_t cpu_ls, uint8_t *fb)
-{
-    if (!is_level_reg(reg)) return tia_poke<VERIFY>(s, T, reg, v, cyc_after, cpu_ls, fb);
-    if (poke_quick_pending(s, reg, v)) return 0;
-    int n = s.nlog;
-    if (n == LOG_CAP) { tia_flush<VERIFY>(s, T, fb); n = 0; }
-    s.log_t[n] = cyc_after;
-    s.log_e[n] = reg | ((v & 0xFF) << 8) | (((cyc_after - cpu_ls) % LINE_CYCLES) << 16);
-    s.log_mask[reg >> 5] |= 1u << (reg & 31);
-    s.nlog = (uint8_t)(n + 1);
     return 0;
 }
 
@@ -765,7 +710,6 @@ __device__ __noinline__ uint32_t tia_poke_deferred(Chip &s, const Tables &T, uin
 template <bool VERIFY>
 __device__ __noinline__ uint32_t tia_peek_cx(Chip &s, const Tables &T, uint32_t reg, uint32_t cyc_after, uint8_t *fb)
 {
-    if (s.nlog) tia_flush<VERIFY>(s, T, fb);
     tia_catchup<VERIFY>(s, T, 3 * (int)(cyc_after - s.tia_ls), fb);
     uint32_t v = (((s.cx >> (2 * reg + 1)) & 1u) << 7) | (((s.cx >> (2 * reg)) & 1u) << 6);
     if (reg == 6) v &= 0x80;
@@ -848,13 +792,12 @@ __device__ __noinline__ uint32_t io_read_slow(Chip &s, const Tables &T, uint32_t
     return tia_peek<VERIFY>(s, T, addr, cyc_after, dbus, fb);
 }
 // returns stall cycles | (frame_done << 16)
-template <bool VERIFY, bool DEFER>
+template <bool VERIFY>
 __device__ __noinline__ uint32_t io_write_slow(Chip &s, const Tables &T, uint32_t addr, uint32_t v, uint32_t cyc_after, uint32_t cpu_ls, uint8_t *fb)
 {
     if (!(addr & 0x1080)) {
         const uint32_t reg = addr & 0x3F;
         if (reg == 0x02) return wsync_stall(cyc_after, cpu_ls);
-        if (DEFER) return tia_poke_deferred<VERIFY>(s, T, reg, v, cyc_after, cpu_ls, fb) | ((uint32_t)s.frame_done << 16);
         if (poke_quick(s, reg, v)) return 0;
         const uint32_t stall = tia_poke<VERIFY>(s, T, reg, v, cyc_after, cpu_ls, fb);
         return stall | ((uint32_t)s.frame_done << 16);

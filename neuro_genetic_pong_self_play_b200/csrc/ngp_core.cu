@@ -166,7 +166,7 @@ __global__ void env_digest_kernel(const Snapshot *envs, int n, uint32_t *out)
 // Fused rollout: one environment (= one game of one genome) per thread.  Lanes are persistent and
 // pull the next environment from a global counter at frame boundaries, so a warp stays in
 // scanline lock-step whatever episode each of its lanes is in.
-template <int CORE, bool SYNC, bool DEFER>
+template <int CORE, bool SYNC>
 __global__ void rollout_kernel(RolloutParams p)
 {
     __shared__ Tables T;
@@ -192,7 +192,7 @@ __global__ void rollout_kernel(RolloutParams p)
         else if (__all_sync(0xFFFFFFFFu, !active)) break;
         if (SYNC || active) {
             double reward;
-            const bool done = roll::episode_frame<CORE, SYNC, DEFER>(ep, p, s, r, T, ram, &reward, active);
+            const bool done = roll::episode_frame<CORE, SYNC>(ep, p, s, r, T, ram, &reward, active);
             if (active) my_frames++;
             if (done) {
                 p.rewards[ep.env] = reward;
@@ -388,10 +388,7 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
     // tuning overrides (experiments only)
     if (const char *e = getenv("NGP_ROLLOUT_BLOCK")) { int b = atoi(e); if (b >= 32 && b <= 1024 && b % 32 == 0) block = b; }
     const bool sync = p.core && block > 32 && !getenv("NGP_ROLLOUT_NOSYNC");
-    const bool defer = sync ? !getenv("NGP_ROLLOUT_NODEFER") : getenv("NGP_ROLLOUT_DEFER") != nullptr;
-    auto kernel = !p.core ? rollout_kernel<0, false, false>
-                          : (sync ? (defer ? rollout_kernel<1, true, true> : rollout_kernel<1, true, false>)
-                                  : (defer ? rollout_kernel<1, false, true> : rollout_kernel<1, false, false>));
+    auto kernel = !p.core ? rollout_kernel<0, false> : (sync ? rollout_kernel<1, true> : rollout_kernel<1, false>);
     long long blocks = (total + block - 1) / block;
     const size_t smem = (size_t)block * 32 * 4;
     int per_sm = 0;

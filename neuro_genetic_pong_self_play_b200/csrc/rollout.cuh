@@ -155,7 +155,7 @@ __device__ __forceinline__ void episode_begin(Episode &ep, const RolloutParams &
 // then *reward holds main.py:109-112's value.
 // `active` = this lane owns an environment; with SYNC every thread of the CTA must come through here (the
 // frame contains CTA-wide barriers), inactive lanes only take part in the barriers.
-template <int CORE, bool SYNC = false, bool DEFER = false>
+template <int CORE, bool SYNC = false>
 __device__ __forceinline__ bool episode_frame(Episode &ep, const RolloutParams &p, Chip &s, CpuRegs &r, const Tables &T, Ram ram,
                                               double *reward, bool active = true)
 {
@@ -165,7 +165,7 @@ __device__ __forceinline__ bool episode_frame(Episode &ep, const RolloutParams &
         a26::apply_input(s, p.needed, 0x3F, fire, dec, inc);
         a26::clear_obs(s);
     }
-    if (CORE) a26::run_frame_compiled<false, SYNC, DEFER>(s, r, T, ram, nullptr, active);
+    if (CORE) a26::run_frame_compiled<false, SYNC>(s, r, T, ram, nullptr, active);
     else if (active) a26::run_frame<false>(s, r, T, ram, nullptr);
     if (!active) return false;
     const int s1 = (int)ram.rd(13), s2 = (int)ram.rd(14);          // score1 = $8D, score2 = $8E

@@ -144,8 +144,7 @@ int hs_env_step_fast(void *h, int core, const uint8_t *action16, uint8_t *ram_ou
     roll::action_to_input(action16, fire, dec, inc);
     a26::apply_input(s, sim->needed.data(), 0x3F, fire, dec, inc);
     a26::clear_obs(s);
-    if (core == 2) a26::run_frame_compiled<false, false, true>(s, sim->r, sim->T, ram, nullptr);
-    else if (core) a26::run_frame_compiled<false, false>(s, sim->r, sim->T, ram, nullptr);
+    if (core) a26::run_frame_compiled<false, false>(s, sim->r, sim->T, ram, nullptr);
     else a26::run_frame<false>(s, sim->r, sim->T, ram, nullptr);
     for (int i = 0; i < 128; ++i) ram_out[i] = (uint8_t)ram.rd(i);
     for (int t = 0; t < 3; ++t) {
@@ -187,8 +186,7 @@ void hs_evaluate(void *h, int core, const int32_t *nodes, int n_layers, int bias
         a26::Chip s; a26::CpuRegs r;
         roll::episode_begin(ep, p, e, s, r, ram);
         double reward = 0.0;
-        if (core == 2) { while (!roll::episode_frame<1, false, true>(ep, p, s, r, sim->T, ram, &reward)) {} }
-        else if (core) { while (!roll::episode_frame<1>(ep, p, s, r, sim->T, ram, &reward)) {} }
+        if (core) { while (!roll::episode_frame<1>(ep, p, s, r, sim->T, ram, &reward)) {} }
         else { while (!roll::episode_frame<0>(ep, p, s, r, sim->T, ram, &reward)) {} }
         rewards[e] = reward; frames[e] = ep.frame;
     }

@@ -262,12 +262,7 @@ class Gen:
             if reg == 0x02:                      # WSYNC: park until the end of the scanline, leave the block
                 e(f"cyc += {cyc}u; cyc += wsync_stall(cyc, cpu_ls); pc = 0x{nxt:04X}u; goto a26_next_;")
                 return True
-            level = (0x04 <= reg <= 0x0F) or (0x1B <= reg <= 0x1F) or (0x25 <= reg <= 0x27)
-            if level:   # latch write: queued until the scanline boundary unless provably invisible
-                e(f"if (DEFER) {{ if (!poke_quick_pending(s, 0x{reg:02X}u, {val})) tia_poke_deferred<VERIFY>(s, T, 0x{reg:02X}u, {val}, cyc + {cyc}u, cpu_ls, fb); }}")
-                e(f"else if (!poke_quick(s, 0x{reg:02X}u, {val})) tia_poke<VERIFY>(s, T, 0x{reg:02X}u, {val}, cyc + {cyc}u, cpu_ls, fb);")
-            else:
-                e(f"if ((DEFER && s.nlog) || !poke_quick(s, 0x{reg:02X}u, {val})) stall_ = tia_poke<VERIFY>(s, T, 0x{reg:02X}u, {val}, cyc + {cyc}u, cpu_ls, fb);")
+            e(f"if (!poke_quick(s, 0x{reg:02X}u, {val})) stall_ = tia_poke<VERIFY>(s, T, 0x{reg:02X}u, {val}, cyc + {cyc}u, cpu_ls, fb);")
             e(f"cyc += {cyc}u + stall_;")
             if reg == 0x00:
                 e(f"if (s.frame_done) {{ done = 1; pc = 0x{nxt:04X}u; goto a26_next_; }}")
