@@ -166,8 +166,8 @@ __global__ void env_digest_kernel(const Snapshot *envs, int n, uint32_t *out)
 // Fused rollout: one environment (= one game of one genome) per thread.  Lanes are persistent and
 // pull the next environment from a global counter at frame boundaries, so a warp stays in
 // scanline lock-step whatever episode each of its lanes is in.
-template <int CORE, bool SYNC>
-__global__ void rollout_kernel(RolloutParams p)
+template <int CORE, bool SYNC, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) rollout_kernel(RolloutParams p)
 {
     __shared__ Tables T;
     extern __shared__ uint32_t ram_smem[];
@@ -388,7 +388,10 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
     // tuning overrides (experiments only)
     if (const char *e = getenv("NGP_ROLLOUT_BLOCK")) { int b = atoi(e); if (b >= 32 && b <= 1024 && b % 32 == 0) block = b; }
     const bool sync = p.core && block > 32 && !getenv("NGP_ROLLOUT_NOSYNC");
-    auto kernel = !p.core ? rollout_kernel<0, false> : (sync ? rollout_kernel<1, true> : rollout_kernel<1, false>);
+    // register budget: MAXT=384 leaves the compiler its ~165 registers; MAXT=512 caps them at 128 (16 warps per SM)
+    const bool lean = sync && (block > 384 || getenv("NGP_ROLLOUT_LEAN"));
+    auto kernel = !p.core ? rollout_kernel<0, false, 384>
+                          : (sync ? (lean ? rollout_kernel<1, true, 512> : rollout_kernel<1, true, 384>) : rollout_kernel<1, false, 384>);
     long long blocks = (total + block - 1) / block;
     const size_t smem = (size_t)block * 32 * 4;
     int per_sm = 0;
