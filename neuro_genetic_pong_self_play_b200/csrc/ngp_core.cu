@@ -388,13 +388,18 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
     // tuning overrides (experiments only)
     if (const char *e = getenv("NGP_ROLLOUT_BLOCK")) { int b = atoi(e); if (b >= 32 && b <= 1024 && b % 32 == 0) block = b; }
     const bool sync = p.core && block > 32 && !getenv("NGP_ROLLOUT_NOSYNC");
-    // register budget: MAXT=384 leaves the compiler its ~165 registers; MAXT=512 caps them at 128 (16 warps per SM)
-    const bool lean = sync && (block > 384 || getenv("NGP_ROLLOUT_LEAN"));
+    // register budget: MAXT=384 leaves the compiler its ~165 registers; MAXT=512 caps them at 128 (16 warps per SM),
+    // MAXT=640 at 96 (20 warps per SM)
+    int lean = sync ? 1 : 0;
+    if (const char *e = getenv("NGP_ROLLOUT_LEAN")) lean = atoi(e);
+    if (!sync) lean = 0;
     auto kernel = !p.core ? rollout_kernel<0, false, 384>
-                          : (sync ? (lean ? rollout_kernel<1, true, 512> : rollout_kernel<1, true, 384>) : rollout_kernel<1, false, 384>);
+                          : (!sync ? rollout_kernel<1, false, 384>
+                                   : (lean == 2 ? rollout_kernel<1, true, 640> : lean == 1 ? rollout_kernel<1, true, 512> : rollout_kernel<1, true, 384>));
     long long blocks = (total + block - 1) / block;
     const size_t smem = (size_t)block * 32 * 4;
     int per_sm = 0;
+    if (smem + sizeof(Tables) > 48 * 1024) NGP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
     if (per_sm < 1) per_sm = 1;
     if (const char *e = getenv("NGP_ROLLOUT_BLOCKS_PER_SM")) { int b = atoi(e); if (b >= 1 && b < per_sm) per_sm = b; }
