@@ -104,6 +104,7 @@ __global__ void env_reset_kernel(const Snapshot *start, Snapshot *envs, int n)
     if (i < n) envs[i] = *start;
 }
 
+template <bool VERIFY>
 __global__ void __launch_bounds__(32) env_step_kernel(const Tables *tables, const uint32_t *needed, Snapshot *envs, int n, int core,
                                                       const uint8_t *actions, uint8_t *fb, uint8_t *ram_out, float *loc,
                                                       uint8_t *valid, uint8_t *regs, unsigned long long *counters)
@@ -121,8 +122,8 @@ __global__ void __launch_bounds__(32) env_step_kernel(const Tables *tables, cons
     a26::apply_input(s, needed, 0x3F, fire, dec, inc);
     a26::clear_obs(s);
     uint8_t *my_fb = fb ? fb + (size_t)e * a26::FB_ROWS * a26::FB_COLS : nullptr;
-    if (core) a26::run_frame_compiled<true, false>(s, r, T, ram, my_fb);
-    else a26::run_frame<true>(s, r, T, ram, my_fb);
+    if (core) a26::run_frame_compiled<VERIFY, false>(s, r, T, ram, my_fb);
+    else a26::run_frame<VERIFY>(s, r, T, ram, my_fb);
     store_snapshot(&envs[e], s, r, ram);
     if (s.error) atomicAdd(&counters[2], 1ull);
     if (ram_out) for (int i = 0; i < 128; ++i) ram_out[(size_t)e * 128 + i] = (uint8_t)ram.rd(i);
@@ -322,8 +323,13 @@ extern "C" int ngp_env_step_core(ngp_handle *h, int32_t core, const uint8_t *act
     const int n = h->n_envs;
     const size_t px = (size_t)n * a26::FB_ROWS * a26::FB_COLS;
     if (frames) NGP_CUDA(cudaMemsetAsync(h->d_fb, 0, px, st));
-    env_step_kernel<<<(n + 31) / 32, 32, 0, st>>>(h->d_tables, h->d_needed, h->d_envs, n, core ? 1 : 0, actions, frames ? h->d_fb : nullptr, ram,
-                                                  loc, valid, regs, h->d_counters);
+    // with a frame requested every pixel is rendered (verify mode); without, the fused no-framebuffer flavour runs
+    if (frames)
+        env_step_kernel<true><<<(n + 31) / 32, 32, 0, st>>>(h->d_tables, h->d_needed, h->d_envs, n, core ? 1 : 0, actions, h->d_fb, ram,
+                                                            loc, valid, regs, h->d_counters);
+    else
+        env_step_kernel<false><<<(n + 31) / 32, 32, 0, st>>>(h->d_tables, h->d_needed, h->d_envs, n, core ? 1 : 0, actions, nullptr, ram,
+                                                             loc, valid, regs, h->d_counters);
     h->launches++;
     NGP_CUDA(cudaGetLastError());
     if (frames) {
@@ -384,7 +390,7 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
     // all SM sub-partitions), larger CTAs in multiples of the SM count once they do
     int block = 32;
     long long warps = (total + 31) / 32;
-    if (warps > (long long)h->sm_count * 16) block = p.core ? 256 : 128;   // CTA-synchronous mode: bigger CTAs share instruction fetches
+    if (warps > (long long)h->sm_count * 16) block = p.core ? 512 : 128;   // CTA-synchronous mode: one 16-warp CTA per SM shares instruction fetches
     // tuning overrides (experiments only)
     if (const char *e = getenv("NGP_ROLLOUT_BLOCK")) { int b = atoi(e); if (b >= 32 && b <= 1024 && b % 32 == 0) block = b; }
     const bool sync = p.core && block > 32 && !getenv("NGP_ROLLOUT_NOSYNC");

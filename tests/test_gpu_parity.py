@@ -294,3 +294,29 @@ def test_ga_step_philox_statistics(ngp):
     d = (a["genomes"] - genomes[a["parent_idx"].long()]).cpu().numpy()
     assert abs(d.std() - np.sqrt(0.9 * 0.81 * 0.9 + 0.0)) < 0.35         # mutation noise present, finite
     eng.close()
+
+
+def test_env_step_fast_flavour_equals_verify_flavour(ngp):
+    """ngp_env_step without a frame request runs the fused no-framebuffer flavour (quick span accounting);
+    RAM and observation must equal the pixel-rendering flavour frame by frame."""
+    rng = np.random.RandomState(8)
+    n, frames = 64, 400
+    acts = np.zeros((frames, n, 16), np.uint8); acts[:, :, 0] = 1; acts[:, :, 15] = 1
+    for f in range(frames):
+        if f % 6 == 0:
+            r = rng.randint(0, 3, n); l = rng.randint(0, 3, n)
+        acts[f, :, 4] = r == 1; acts[f, :, 5] = r == 2; acts[f, :, 6] = l == 1; acts[f, :, 7] = l == 2
+    outs = []
+    for want_frames, core in ((True, ngp.CORE_INTERPRETER), (False, ngp.CORE_TRANSLATED), (False, ngp.CORE_INTERPRETER)):
+        eng = ngp.Engine(ngp.Config(), device=0)
+        eng.env_reset(n, ngp.STATE_START_2P)
+        rec = []
+        for f in range(frames):
+            o = eng.env_step(torch.from_numpy(acts[f]).cuda(), want_frames=want_frames, core=core)
+            rec.append((o["ram"].clone(), o["loc"] * o["valid"][..., None], o["valid"].clone()))
+        outs.append(rec)
+        eng.close()
+    for f in range(frames):
+        for k in (1, 2):
+            assert torch.equal(outs[0][f][0], outs[k][f][0]), f"RAM frame {f}"
+            assert torch.equal(outs[0][f][2], outs[k][f][2]) and torch.equal(outs[0][f][1], outs[k][f][1]), f"observation frame {f}"
