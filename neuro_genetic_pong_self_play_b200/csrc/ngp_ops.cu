@@ -22,21 +22,37 @@ __global__ void __launch_bounds__(256) find_stuff_kernel(const uint8_t *__restri
     for (int f = blockIdx.x; f < n; f += gridDim.x) {
         const uint4 *src = reinterpret_cast<const uint4 *>(frames + (size_t)f * (a26::FB_ROWS * 480) + a26::CROP_TOP * 480);
         uint32_t acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};       // per target: count, sum row, sum col
-        for (int k = threadIdx.x; k < VEC_PER_FRAME; k += 256) {
-            const uint4 v = __ldg(&src[k]);
-            const uint32_t words[4] = {v.x, v.y, v.z, v.w};
-            const int phase = k % 3, row = k / 30, byte0 = (k % 30) * 16;
+        // 4800 vectors per frame, 256 threads: 19 rounds; loads are issued four at a time before any compare so
+        // that each thread keeps 64 B in flight (the kernel is a pure HBM stream)
+        constexpr int ROUNDS = (VEC_PER_FRAME + 255) / 256;
+#pragma unroll 1
+        for (int r0 = 0; r0 < ROUNDS; r0 += 4) {
+            uint4 vec[4];
+            bool ok[4];
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
+            for (int j = 0; j < 4; ++j) {
+                const int k = threadIdx.x + (r0 + j) * 256;
+                ok[j] = (r0 + j) < ROUNDS && k < VEC_PER_FRAME;
+                if (ok[j]) vec[j] = __ldcs(&src[k]);
+            }
 #pragma unroll
-                for (int wi = 0; wi < 4; ++wi) {
-                    uint32_t m = __vcmpeq4(words[wi], pat.w[phase][t][wi]) & 0x01010101u;
-                    if (m) {
-                        const int b = byte0 + wi * 4;
-                        uint32_t c = __popc(m);
-                        uint32_t sc = (m & 1) * (b / 3) + ((m >> 8) & 1) * ((b + 1) / 3) + ((m >> 16) & 1) * ((b + 2) / 3) +
-                                      ((m >> 24) & 1) * ((b + 3) / 3);
-                        acc[3 * t] += c; acc[3 * t + 1] += c * row; acc[3 * t + 2] += sc;
+            for (int j = 0; j < 4; ++j) {
+                if (!ok[j]) continue;
+                const int k = threadIdx.x + (r0 + j) * 256;
+                const uint32_t words[4] = {vec[j].x, vec[j].y, vec[j].z, vec[j].w};
+                const int phase = k % 3, row = k / 30, byte0 = (k % 30) * 16;
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+#pragma unroll
+                    for (int wi = 0; wi < 4; ++wi) {
+                        uint32_t m = __vcmpeq4(words[wi], pat.w[phase][t][wi]) & 0x01010101u;
+                        if (m) {
+                            const int b = byte0 + wi * 4;
+                            uint32_t c = __popc(m);
+                            uint32_t sc = (m & 1) * (b / 3) + ((m >> 8) & 1) * ((b + 1) / 3) + ((m >> 16) & 1) * ((b + 2) / 3) +
+                                          ((m >> 24) & 1) * ((b + 3) / 3);
+                            acc[3 * t] += c; acc[3 * t + 1] += c * row; acc[3 * t + 2] += sc;
+                        }
                     }
                 }
             }
