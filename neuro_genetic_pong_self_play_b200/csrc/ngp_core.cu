@@ -386,11 +386,16 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
     p.time_scaler = (double)h->cfg.time_scaler; p.paddle_height = (double)h->cfg.scaled_paddle_height;
     p.seed = seed; p.generation = generation; p.shape = h->shape;
     p.rewards = rewards ? rewards : h->d_rewards; p.frames = frames ? frames : h->d_frames; p.counters = h->d_counters;
-    // launch geometry: one warp per CTA while the environments do not fill the GPU (spreads warps over
-    // all SM sub-partitions), larger CTAs in multiples of the SM count once they do
+    // Launch geometry (measured, profiles/README.md).  Small launches: one-warp CTAs spread over all SMs.  From ~2 warps per
+    // SM upwards the CTA-synchronous flavour wins: all warps of a CTA walk through the frame together and share their
+    // instruction fetches; the CTA grows with the launch until one 16-warp CTA per SM (128 registers/thread) is reached.
     int block = 32;
     long long warps = (total + 31) / 32;
-    if (warps > (long long)h->sm_count * 16) block = p.core ? 512 : 128;   // CTA-synchronous mode: one 16-warp CTA per SM shares instruction fetches
+    if (p.core) {
+        if (total >= 73728) block = 512;
+        else if (total >= 36864) block = 256;
+        else if (total >= 12288) block = 128;
+    } else if (warps > (long long)h->sm_count * 16) block = 128;
     // tuning overrides (experiments only)
     if (const char *e = getenv("NGP_ROLLOUT_BLOCK")) { int b = atoi(e); if (b >= 32 && b <= 1024 && b % 32 == 0) block = b; }
     const bool sync = p.core && block > 32 && !getenv("NGP_ROLLOUT_NOSYNC");

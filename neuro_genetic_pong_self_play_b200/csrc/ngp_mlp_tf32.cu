@@ -1,0 +1,203 @@
+// ngp_mlp_tf32.cu -- K3 wide layers on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// One hidden layer of the per-genome MLP (numpy_nn.NeuralNetwork.run, /root/reference/numpy_nn.py:126-129) for
+// E environments of one genome is a small dense contraction  out[e][o] = sigmoid( sum_k W_g[o][k] * a[e][k] )
+// with W_g = that genome's (n_out x (n_in+1)) slice of the genome vector (bias weight = last column).  For the
+// [6,512,512,2] net and 64 environments per genome (BASELINE config 4) the 512x513 layer is 98 % of the FLOPs and
+// its 1.05 MB of weights are used for one step only: the layer is bound by streaming weights from HBM, which FP32
+// FFMA cannot keep up with (34 MFLOP per MB) but tensor cores can.
+//
+// Mapping (D^T form, so nothing is padded): CTA = 128 outputs x 64 environments of one genome.
+//   A (UMMA "M" side) = weights  [128 outputs][K]  -- K-major exactly as the genome stores them
+//   B (UMMA "N" side) = inputs   [ 64 envs   ][K]  -- K-major, bias column synthesised as 1.0, zero padding
+//   D (TMEM)          = [128 lanes = outputs][64 columns = envs], FP32
+// Precision: kind::tf32 keeps 10 mantissa bits, which cannot meet the reference tolerance (rtol 1e-5), so every
+// operand is split x = hi + lo with hi = tf32(x) and the product is accumulated as hi*hi + lo*hi + hi*lo
+// ("3xTF32", relative error ~2^-21).  Three MMAs per k-step still leave the layer HBM-bound (96 flop/B against a
+// ridge of ~170 flop/B), so the split costs no time.
+// Pipeline: K is walked in chunks of 32 floats through two shared-memory stages.  All 256 threads load a chunk
+// (coalesced 128-byte rows), split it and store hi/lo tiles in the canonical no-swizzle K-major core-matrix
+// layout; one thread issues the 12 tcgen05.mma of the chunk and commits them to the stage's mbarrier, which is
+// what the loaders of chunk i+2 wait on.  The epilogue reads TMEM with tcgen05.ld (warp w owns lanes 32w..32w+31),
+// applies the sigmoid and writes out[e][o] coalesced along o.
+#include "ngp_internal.h"
+
+namespace tf32 {
+
+constexpr int TM = 128;            // outputs per CTA  (UMMA M)
+constexpr int TN = 64;             // environments per CTA (UMMA N)
+constexpr int KC = 32;             // floats per K chunk = 8 chunks of 16 bytes = 4 MMAs of K=8
+constexpr int THREADS = 256;
+// canonical K-major, no swizzle: 16-byte unit (row r, k-unit c) at  c*LBO + (r/8)*SBO + (r%8)*16
+constexpr uint32_t SBO = 128;                              // next group of 8 rows
+constexpr uint32_t LBO_A = TM * 16 + 16;                   // next 16-byte k unit (+16 B pad: conflict-free stores)
+constexpr uint32_t LBO_B = TN * 16 + 16;
+constexpr uint32_t TILE_A = (KC / 4) * LBO_A;              // bytes of one A tile (hi or lo)
+constexpr uint32_t TILE_B = (KC / 4) * LBO_B;
+constexpr uint32_t STAGE = 2 * TILE_A + 2 * TILE_B;        // A_hi, A_lo, B_hi, B_lo
+constexpr uint32_t SMEM_BYTES = 2 * STAGE + 64;
+constexpr uint32_t TMEM_COLS = 64;
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N=64, M=128
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo)
+{
+    // cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout NONE
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// in[g][e][ni] (+ bias 1) x W_g[no][ni+bias] -> out[g][e][no] = sigmoid(.)
+__global__ void __launch_bounds__(THREADS, 1)
+mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, const float *__restrict__ in, int envs, int ni, int no, int bias,
+                      float *__restrict__ out)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.z, e0 = blockIdx.y * TN, o0 = blockIdx.x * TM;
+    const int K = ni + bias;
+    const int n_chunks = (K + KC - 1) / KC;
+    const float *W = genomes + (size_t)g * G + w_off;
+    const float *A = in + (size_t)g * envs * ni;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar0 = smem_base + 2 * STAGE;            // two stage barriers + one "accumulator ready" barrier
+    const uint32_t bar_done = bar0 + 16;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;
+
+    for (int c = 0; c < n_chunks; ++c) {
+        const int st = c & 1;
+        uint8_t *stage = smem + st * STAGE;
+        // the MMAs that read this stage two chunks ago must have completed
+        if (c >= 2) mbar_wait(bar0 + 8 * st, ((c >> 1) - 1) & 1);
+        const int k = c * KC + lane;                        // this lane's column of the chunk
+        const uint32_t unit = (uint32_t)(lane >> 2), sub = (uint32_t)(lane & 3) * 4;
+        // weights: warp w loads rows w, w+8, ...  (one coalesced 128-byte row segment per load)
+#pragma unroll 4
+        for (int r = warp; r < TM; r += THREADS / 32) {
+            float x = 0.f;
+            if (o0 + r < no && k < K) x = __ldg(&W[(size_t)(o0 + r) * K + k]);
+            const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u), lo = x - hi;
+            const uint32_t off = unit * LBO_A + (uint32_t)(r >> 3) * SBO + (uint32_t)(r & 7) * 16 + sub;
+            *reinterpret_cast<float *>(stage + off) = hi;
+            *reinterpret_cast<float *>(stage + TILE_A + off) = lo;
+        }
+        // inputs: bias column = 1.0, padding = 0
+#pragma unroll 4
+        for (int r = warp; r < TN; r += THREADS / 32) {
+            float x = 0.f;
+            if (e0 + r < envs) {
+                if (k < ni) x = __ldg(&A[(size_t)(e0 + r) * ni + k]);
+                else if (k == ni && bias) x = 1.0f;
+            }
+            const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u), lo = x - hi;
+            const uint32_t off = unit * LBO_B + (uint32_t)(r >> 3) * SBO + (uint32_t)(r & 7) * 16 + sub;
+            *reinterpret_cast<float *>(stage + 2 * TILE_A + off) = hi;
+            *reinterpret_cast<float *>(stage + 2 * TILE_A + TILE_B + off) = lo;
+        }
+        // generic-proxy stores -> visible to the tensor core's async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_base + st * STAGE, a_lo = a_hi + TILE_A, b_hi = a_hi + 2 * TILE_A, b_lo = b_hi + TILE_B;
+#pragma unroll
+            for (int j = 0; j < KC / 8; ++j) {             // one MMA consumes two 16-byte k units
+                const uint32_t ka = 2 * j * LBO_A, kb = 2 * j * LBO_B;
+                umma_tf32(tmem_d, make_desc(a_lo + ka, LBO_A), make_desc(b_hi + kb, LBO_B), (c | j) ? 1u : 0u);   // small terms first
+                umma_tf32(tmem_d, make_desc(a_hi + ka, LBO_A), make_desc(b_lo + kb, LBO_B), 1u);
+                umma_tf32(tmem_d, make_desc(a_hi + ka, LBO_A), make_desc(b_hi + kb, LBO_B), 1u);
+            }
+            umma_commit(bar0 + 8 * st);                     // stage reusable when these MMAs are done
+            if (c == n_chunks - 1) umma_commit(bar_done);   // accumulator complete
+        }
+    }
+    // ---- epilogue: TMEM -> registers -> sigmoid -> out[e][o] ----
+    mbar_wait(bar_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp < 4) {
+        const int o = o0 + warp * 32 + lane;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(half * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (o < no) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int e = e0 + half * 32 + j;
+                    if (e < envs) out[((size_t)g * envs + e) * no + o] = 1.0f / (1.0f + expf(-__uint_as_float(v[j])));
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+}
+
+}  // namespace tf32
+
+// Launch one wide hidden layer on the tensor-core path; returns NGP_ERR_UNSUPPORTED when the shape does not
+// make it a real dense contraction (callers then use the FP32 FFMA kernel).
+int ngp_mlp_layer_tf32(ngp_handle *h, const float *genomes, size_t w_off, const float *in, int n_genomes, int envs, int ni, int no, int bias,
+                       float *out, cudaStream_t st)
+{
+    if (ni < 64 || no < 64 || envs < 16) return NGP_ERR_UNSUPPORTED;
+    static bool attr_set[64];
+    if (!attr_set[h->device]) {
+        NGP_CUDA(cudaFuncSetAttribute(tf32::mlp_layer_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf32::SMEM_BYTES));
+        attr_set[h->device] = true;
+    }
+    dim3 grid((no + tf32::TM - 1) / tf32::TM, (envs + tf32::TN - 1) / tf32::TN, n_genomes);
+    tf32::mlp_layer_tf32_kernel<<<grid, tf32::THREADS, tf32::SMEM_BYTES, st>>>(genomes, w_off, h->gene_size, in, envs, ni, no, bias, out);
+    h->launches++;
+    NGP_CUDA(cudaGetLastError());
+    return NGP_OK;
+}

@@ -4,6 +4,7 @@
 //   K4  GA step                       DEAP selTournament / cxBlend / mutGaussian / varAnd as wired in
 //                                     ga.py:85-94 and driven by eaSimple at main.py:165-170
 #include <math.h>
+#include <stdlib.h>
 
 #include "ngp_internal.h"
 
@@ -223,6 +224,9 @@ __global__ void mlp_decide_kernel(const double *__restrict__ z, long long rows, 
     act[r] = best == 0 ? pol::ACT_UP : pol::ACT_DOWN;
 }
 
+int ngp_mlp_layer_tf32(ngp_handle *h, const float *genomes, size_t w_off, const float *in, int n_genomes, int envs, int ni, int no, int bias,
+                       float *out, cudaStream_t st);   // ngp_mlp_tf32.cu
+
 struct MlpScratch { float *a, *b; double *z; size_t cap_ab, cap_z; };
 static MlpScratch g_mlp_scratch[64];   // per device
 
@@ -262,10 +266,19 @@ extern "C" int ngp_mlp_forward(ngp_handle *h, const float *genomes, const float 
     for (int l = 0; l < L; ++l) {
         const int ni = sh.nodes[l], no = sh.nodes[l + 1];
         dim3 grid((no + 63) / 64, (envs + 63) / 64, n_genomes);
-        if (l == L - 1) mlp_layer_kernel<true><<<grid, 256, 0, st>>>(genomes, w_off, h->gene_size, in, envs, ni, no, bias, nullptr, sc.z);
-        else mlp_layer_kernel<false><<<grid, 256, 0, st>>>(genomes, w_off, h->gene_size, in, envs, ni, no, bias, bufs[l & 1], nullptr);
-        h->launches++;
-        NGP_CUDA(cudaGetLastError());
+        bool launched = false;
+        if (l != L - 1 && !getenv("NGP_MLP_NO_TF32")) {
+            // wide hidden layer with enough environments per genome: tensor cores (3xTF32, tcgen05 + TMEM)
+            const int rc = ngp_mlp_layer_tf32(h, genomes, w_off, in, n_genomes, envs, ni, no, bias, bufs[l & 1], st);
+            if (rc == NGP_OK) launched = true;
+            else if (rc != NGP_ERR_UNSUPPORTED) return rc;
+        }
+        if (!launched) {
+            if (l == L - 1) mlp_layer_kernel<true><<<grid, 256, 0, st>>>(genomes, w_off, h->gene_size, in, envs, ni, no, bias, nullptr, sc.z);
+            else mlp_layer_kernel<false><<<grid, 256, 0, st>>>(genomes, w_off, h->gene_size, in, envs, ni, no, bias, bufs[l & 1], nullptr);
+            h->launches++;
+            NGP_CUDA(cudaGetLastError());
+        }
         in = bufs[l & 1];
         w_off += (size_t)(ni + bias) * no;
     }

@@ -320,3 +320,31 @@ def test_env_step_fast_flavour_equals_verify_flavour(ngp):
         for k in (1, 2):
             assert torch.equal(outs[0][f][0], outs[k][f][0]), f"RAM frame {f}"
             assert torch.equal(outs[0][f][2], outs[k][f][2]) and torch.equal(outs[0][f][1], outs[k][f][1]), f"observation frame {f}"
+
+
+@pytest.mark.parametrize("nodes,envs", [((6, 512, 512, 2), 64), ((6, 512, 512, 2), 40), ((6, 128, 192, 2), 64), ((6, 64, 64, 64, 2), 17)])
+def test_mlp_forward_tensor_core_path(ngp, nodes, envs):
+    """Wide hidden layers with >= 16 environments per genome run on tcgen05 (3xTF32, TMEM accumulators).  Tolerance:
+    rtol 1e-5 against the FP64 oracle (the north_star's FP32 bar; plain TF32 would be ~1e-3), argmax 100 %; the
+    FP32 FFMA path must agree to the same tolerance.  Ragged shapes: envs not a multiple of 64, outputs not of 128."""
+    import oracle
+    eng = ngp.Engine(ngp.Config(NETWORK_SHAPE=nodes), device=0)
+    rng = np.random.RandomState(envs)
+    n = 3
+    genomes = (rng.standard_normal((n, eng.gene_size)) * 0.08).astype(np.float32)
+    x = rng.random_sample((n, envs, 6)).astype(np.float32)
+    act, out = eng.mlp_forward(torch.from_numpy(genomes).cuda(), torch.from_numpy(x).cuda())
+    os.environ["NGP_MLP_NO_TF32"] = "1"
+    try:
+        act_f, out_f = eng.mlp_forward(torch.from_numpy(genomes).cuda(), torch.from_numpy(x).cuda())
+    finally:
+        del os.environ["NGP_MLP_NO_TF32"]
+    ref_out = np.zeros((n, envs, nodes[-1])); ref_act = np.zeros((n, envs), np.uint8)
+    for g in range(n):
+        for e in range(envs):
+            o, a = oracle.mlp_forward(list(nodes), genomes[g], x[g, e].astype(np.float64))
+            ref_out[g, e] = o; ref_act[g, e] = a
+    np.testing.assert_allclose(out.cpu().numpy(), ref_out, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(out_f.cpu().numpy(), ref_out, rtol=1e-5, atol=1e-7)
+    assert np.array_equal(act.cpu().numpy(), ref_act) and np.array_equal(act_f.cpu().numpy(), ref_act)
+    eng.close()
