@@ -101,36 +101,52 @@ mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, co
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_slot;
 
+    // Register-staged producer: the 24 values a thread contributes to a chunk (16 weight rows, 8 input rows) are
+    // loaded with all loads in flight at once, one chunk ahead of the shared-memory stores.
+    constexpr int WR = TM / (THREADS / 32), XR = TN / (THREADS / 32);      // rows per warp: 16 and 8
+    float wv[WR], xv[XR];
+    auto load_chunk = [&](int c) {
+        const int k = c * KC + lane;                        // this lane's column of the chunk
+#pragma unroll
+        for (int i = 0; i < WR; ++i) {
+            const int r = warp + i * (THREADS / 32);
+            wv[i] = (o0 + r < no && k < K) ? __ldg(&W[(size_t)(o0 + r) * K + k]) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < XR; ++i) {
+            const int r = warp + i * (THREADS / 32);
+            float x = 0.f;
+            if (e0 + r < envs) {
+                if (k < ni) x = __ldg(&A[(size_t)(e0 + r) * ni + k]);
+                else if (k == ni && bias) x = 1.0f;          // bias input
+            }
+            xv[i] = x;
+        }
+    };
+    load_chunk(0);
+    const uint32_t unit = (uint32_t)(lane >> 2), sub = (uint32_t)(lane & 3) * 4;
     for (int c = 0; c < n_chunks; ++c) {
         const int st = c & 1;
         uint8_t *stage = smem + st * STAGE;
         // the MMAs that read this stage two chunks ago must have completed
         if (c >= 2) mbar_wait(bar0 + 8 * st, ((c >> 1) - 1) & 1);
-        const int k = c * KC + lane;                        // this lane's column of the chunk
-        const uint32_t unit = (uint32_t)(lane >> 2), sub = (uint32_t)(lane & 3) * 4;
-        // weights: warp w loads rows w, w+8, ...  (one coalesced 128-byte row segment per load)
-#pragma unroll 4
-        for (int r = warp; r < TM; r += THREADS / 32) {
-            float x = 0.f;
-            if (o0 + r < no && k < K) x = __ldg(&W[(size_t)(o0 + r) * K + k]);
-            const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u), lo = x - hi;
+#pragma unroll
+        for (int i = 0; i < WR; ++i) {
+            const int r = warp + i * (THREADS / 32);
+            const float x = wv[i], hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u), lo = x - hi;
             const uint32_t off = unit * LBO_A + (uint32_t)(r >> 3) * SBO + (uint32_t)(r & 7) * 16 + sub;
             *reinterpret_cast<float *>(stage + off) = hi;
             *reinterpret_cast<float *>(stage + TILE_A + off) = lo;
         }
-        // inputs: bias column = 1.0, padding = 0
-#pragma unroll 4
-        for (int r = warp; r < TN; r += THREADS / 32) {
-            float x = 0.f;
-            if (e0 + r < envs) {
-                if (k < ni) x = __ldg(&A[(size_t)(e0 + r) * ni + k]);
-                else if (k == ni && bias) x = 1.0f;
-            }
-            const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u), lo = x - hi;
+#pragma unroll
+        for (int i = 0; i < XR; ++i) {
+            const int r = warp + i * (THREADS / 32);
+            const float x = xv[i], hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u), lo = x - hi;
             const uint32_t off = unit * LBO_B + (uint32_t)(r >> 3) * SBO + (uint32_t)(r & 7) * 16 + sub;
             *reinterpret_cast<float *>(stage + 2 * TILE_A + off) = hi;
             *reinterpret_cast<float *>(stage + 2 * TILE_A + TILE_B + off) = lo;
         }
+        if (c + 1 < n_chunks) load_chunk(c + 1);           // in flight across the barrier, the MMA issue and the next wait
         // generic-proxy stores -> visible to the tensor core's async proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

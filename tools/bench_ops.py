@@ -69,13 +69,18 @@ def main():
     # K3 wide net, 64 envs per genome: weights streamed once per genome
     engw = ngp.Engine(ngp.Config(NETWORK_SHAPE=(6, 512, 512, 2)), device=0)
     G = engw.gene_size
-    for n in (64, 256):
+    for n in (64, 256, 1024):
         g = (torch.randn((n, G), device="cuda") * 0.05)
         x = torch.rand((n, 64, 6), device="cuda")
-        t = timed(lambda: engw.mlp_forward(g, x, want_out=False), iters=5, warm=2)
-        flops = 2.0 * G * 64 * n
-        print(json.dumps({"op": "mlp_forward[6,512,512,2]", "config": {"genomes": n, "envs": 64}, "ms": t * 1e3, "inferences_per_s": n * 64 / t,
-                          "algorithmic_gbs": n * G * 4 / t / 1e9, "hbm_peak_gbs": PEAK, "frac": n * G * 4 / t / 1e9 / PEAK, "tflops_fp32": flops / t / 1e12}), flush=True)
+        for path in ("tcgen05_3xtf32", "fp32_ffma"):
+            if path == "fp32_ffma":
+                os.environ["NGP_MLP_NO_TF32"] = "1"
+            t = timed(lambda: engw.mlp_forward(g, x, want_out=False), iters=5, warm=2)
+            os.environ.pop("NGP_MLP_NO_TF32", None)
+            flops = 2.0 * G * 64 * n
+            print(json.dumps({"op": "mlp_forward[6,512,512,2]", "path": path, "config": {"genomes": n, "envs": 64}, "ms": t * 1e3,
+                              "inferences_per_s": n * 64 / t, "algorithmic_gbs": n * G * 4 / t / 1e9, "hbm_peak_gbs": PEAK,
+                              "frac": n * G * 4 / t / 1e9 / PEAK, "tflops_algorithmic": flops / t / 1e12}), flush=True)
     engw.close()
     # K4: GA step, ~3*N*G*4 bytes
     for logn in (10, 14, 17):
