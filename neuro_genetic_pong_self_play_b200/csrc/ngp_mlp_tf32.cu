@@ -72,7 +72,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 }
 
 // in[g][e][ni] (+ bias 1) x W_g[no][ni+bias] -> out[g][e][no] = sigmoid(.)
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 2)
 mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, const float *__restrict__ in, int envs, int ni, int no, int bias,
                       float *__restrict__ out)
 {
@@ -101,51 +101,70 @@ mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, co
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_slot;
 
-    // Register-staged producer: the 24 values a thread contributes to a chunk (16 weight rows, 8 input rows) are
-    // loaded with all loads in flight at once, one chunk ahead of the shared-memory stores.
-    constexpr int WR = TM / (THREADS / 32), XR = TN / (THREADS / 32);      // rows per warp: 16 and 8
-    float wv[WR], xv[XR];
+    // Register-staged producer.  A thread owns one 16-byte k unit (4 consecutive floats) of 4 weight rows and 2 input rows
+    // per chunk: lane = (row-in-group << 3) | unit.  Rows are not 16-byte aligned in the genome (K = n_in + 1 floats), so
+    // the unit is fetched with four 4-byte loads that share their sectors through L1; it is split into hi/lo and stored
+    // with two 16-byte shared-memory stores (conflict-free: LBO shifts each unit by one 16-byte bank group).
+    constexpr int WI = TM / 32, XI = TN / 32;               // row groups per thread: 4 and 2
+    const int unit = lane & 7, rsub = lane >> 3;
+    const float *wp[WI];
+    bool wok[WI];
+    uint32_t woff[WI];
+#pragma unroll
+    for (int i = 0; i < WI; ++i) {
+        const int r = warp * (TM / 8) + i * 4 + rsub;
+        wok[i] = o0 + r < no;
+        wp[i] = W + (size_t)(wok[i] ? o0 + r : 0) * K + unit * 4;
+        woff[i] = (uint32_t)unit * LBO_A + (uint32_t)(r >> 3) * SBO + (uint32_t)(r & 7) * 16;
+    }
+    const float *xp[XI];
+    bool xok[XI];
+    uint32_t xoff[XI];
+#pragma unroll
+    for (int i = 0; i < XI; ++i) {
+        const int r = warp * (TN / 8) + i * 4 + rsub;
+        xok[i] = e0 + r < envs;
+        xp[i] = A + (size_t)(xok[i] ? e0 + r : 0) * ni + unit * 4;
+        xoff[i] = 2 * TILE_A + (uint32_t)unit * LBO_B + (uint32_t)(r >> 3) * SBO + (uint32_t)(r & 7) * 16;
+    }
+    float wv[WI][4], xv[XI][4];
     auto load_chunk = [&](int c) {
-        const int k = c * KC + lane;                        // this lane's column of the chunk
+        const int k0 = c * KC + unit * 4;                   // first column of this thread's unit
 #pragma unroll
-        for (int i = 0; i < WR; ++i) {
-            const int r = warp + i * (THREADS / 32);
-            wv[i] = (o0 + r < no && k < K) ? __ldg(&W[(size_t)(o0 + r) * K + k]) : 0.f;
-        }
+        for (int i = 0; i < WI; ++i)
 #pragma unroll
-        for (int i = 0; i < XR; ++i) {
-            const int r = warp + i * (THREADS / 32);
-            float x = 0.f;
-            if (e0 + r < envs) {
-                if (k < ni) x = __ldg(&A[(size_t)(e0 + r) * ni + k]);
-                else if (k == ni && bias) x = 1.0f;          // bias input
+            for (int j = 0; j < 4; ++j) wv[i][j] = (wok[i] && k0 + j < K) ? __ldg(wp[i] + c * KC + j) : 0.f;
+#pragma unroll
+        for (int i = 0; i < XI; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float x = 0.f;
+                if (xok[i]) {
+                    if (k0 + j < ni) x = __ldg(xp[i] + c * KC + j);
+                    else if (k0 + j == ni && bias) x = 1.0f;      // bias input
+                }
+                xv[i][j] = x;
             }
-            xv[i] = x;
-        }
+    };
+    auto split_store = [&](uint8_t *tile_hi, uint32_t lo_delta, const float (&v)[4]) {
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u); lo.x = v[0] - hi.x;
+        hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u); lo.y = v[1] - hi.y;
+        hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u); lo.z = v[2] - hi.z;
+        hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u); lo.w = v[3] - hi.w;
+        *reinterpret_cast<float4 *>(tile_hi) = hi;
+        *reinterpret_cast<float4 *>(tile_hi + lo_delta) = lo;
     };
     load_chunk(0);
-    const uint32_t unit = (uint32_t)(lane >> 2), sub = (uint32_t)(lane & 3) * 4;
     for (int c = 0; c < n_chunks; ++c) {
         const int st = c & 1;
         uint8_t *stage = smem + st * STAGE;
         // the MMAs that read this stage two chunks ago must have completed
         if (c >= 2) mbar_wait(bar0 + 8 * st, ((c >> 1) - 1) & 1);
 #pragma unroll
-        for (int i = 0; i < WR; ++i) {
-            const int r = warp + i * (THREADS / 32);
-            const float x = wv[i], hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u), lo = x - hi;
-            const uint32_t off = unit * LBO_A + (uint32_t)(r >> 3) * SBO + (uint32_t)(r & 7) * 16 + sub;
-            *reinterpret_cast<float *>(stage + off) = hi;
-            *reinterpret_cast<float *>(stage + TILE_A + off) = lo;
-        }
+        for (int i = 0; i < WI; ++i) split_store(stage + woff[i], TILE_A, wv[i]);
 #pragma unroll
-        for (int i = 0; i < XR; ++i) {
-            const int r = warp + i * (THREADS / 32);
-            const float x = xv[i], hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u), lo = x - hi;
-            const uint32_t off = unit * LBO_B + (uint32_t)(r >> 3) * SBO + (uint32_t)(r & 7) * 16 + sub;
-            *reinterpret_cast<float *>(stage + 2 * TILE_A + off) = hi;
-            *reinterpret_cast<float *>(stage + 2 * TILE_A + TILE_B + off) = lo;
-        }
+        for (int i = 0; i < XI; ++i) split_store(stage + xoff[i], TILE_B, xv[i]);
         if (c + 1 < n_chunks) load_chunk(c + 1);           // in flight across the barrier, the MMA issue and the next wait
         // generic-proxy stores -> visible to the tensor core's async proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
