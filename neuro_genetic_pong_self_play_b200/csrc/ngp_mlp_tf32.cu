@@ -101,59 +101,30 @@ mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, co
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_slot;
 
-    // Register-staged producer.  A thread owns one 16-byte k unit (4 consecutive floats) of 4 weight rows and 2 input rows
-    // per chunk: lane = (row-in-group << 3) | unit.  Rows are not 16-byte aligned in the genome (K = n_in + 1 floats), so
-    // the unit is fetched with four 4-byte loads that share their sectors through L1; it is split into hi/lo and stored
-    // with two 16-byte shared-memory stores (conflict-free: LBO shifts each unit by one 16-byte bank group).
-    constexpr int WI = TM / 32, XI = TN / 32;               // row groups per thread: 4 and 2
-    const int unit = lane & 7, rsub = lane >> 3;
-    const float *wp[WI];
-    bool wok[WI];
-    uint32_t woff[WI];
+    // Register-staged producer.  lane = column k of the chunk (coalesced 128-byte row segments), warp w owns weight rows
+    // w, w+8, .. and input rows w, w+8, ..; all pointers, predicates and shared-memory offsets are hoisted out of the
+    // chunk loop, the 24 loads of a chunk are all in flight at once and one chunk ahead of the shared-memory stores.
+    constexpr int WR = TM / 8, XR = TN / 8;                 // rows per thread: 16 weight rows, 8 input rows
+    const uint32_t unit = (uint32_t)(lane >> 2), sub = (uint32_t)(lane & 3) * 4;
+    const uint32_t a_off = unit * LBO_A + (uint32_t)warp * 16 + sub;               // row r = warp + 8 i  ->  + i * SBO
+    const uint32_t b_off = 2 * TILE_A + unit * LBO_B + (uint32_t)warp * 16 + sub;
+    const float *wp = W + (size_t)min(o0 + warp, no - 1) * K + lane;
+    const float *xp = A + (size_t)min(e0 + warp, envs - 1) * ni + lane;
+    uint32_t wmask = 0, xmask = 0;                           // rows of this thread that exist
 #pragma unroll
-    for (int i = 0; i < WI; ++i) {
-        const int r = warp * (TM / 8) + i * 4 + rsub;
-        wok[i] = o0 + r < no;
-        wp[i] = W + (size_t)(wok[i] ? o0 + r : 0) * K + unit * 4;
-        woff[i] = (uint32_t)unit * LBO_A + (uint32_t)(r >> 3) * SBO + (uint32_t)(r & 7) * 16;
-    }
-    const float *xp[XI];
-    bool xok[XI];
-    uint32_t xoff[XI];
+    for (int i = 0; i < WR; ++i) wmask |= (o0 + warp + 8 * i < no ? 1u : 0u) << i;
 #pragma unroll
-    for (int i = 0; i < XI; ++i) {
-        const int r = warp * (TN / 8) + i * 4 + rsub;
-        xok[i] = e0 + r < envs;
-        xp[i] = A + (size_t)(xok[i] ? e0 + r : 0) * ni + unit * 4;
-        xoff[i] = 2 * TILE_A + (uint32_t)unit * LBO_B + (uint32_t)(r >> 3) * SBO + (uint32_t)(r & 7) * 16;
-    }
-    float wv[WI][4], xv[XI][4];
+    for (int i = 0; i < XR; ++i) xmask |= (e0 + warp + 8 * i < envs ? 1u : 0u) << i;
+    float wv[WR], xv[XR];
     auto load_chunk = [&](int c) {
-        const int k0 = c * KC + unit * 4;                   // first column of this thread's unit
+        const int k = c * KC + lane;
+        const bool kw = k < K, kx = k < ni;
+        const float fill = (k == ni && bias) ? 1.0f : 0.0f;  // bias input column / zero padding
+        const float *w = wp + c * KC, *x = xp + c * KC;
 #pragma unroll
-        for (int i = 0; i < WI; ++i)
+        for (int i = 0; i < WR; ++i) wv[i] = (kw && ((wmask >> i) & 1)) ? __ldg(w + (size_t)i * 8 * K) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) wv[i][j] = (wok[i] && k0 + j < K) ? __ldg(wp[i] + c * KC + j) : 0.f;
-#pragma unroll
-        for (int i = 0; i < XI; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float x = 0.f;
-                if (xok[i]) {
-                    if (k0 + j < ni) x = __ldg(xp[i] + c * KC + j);
-                    else if (k0 + j == ni && bias) x = 1.0f;      // bias input
-                }
-                xv[i][j] = x;
-            }
-    };
-    auto split_store = [&](uint8_t *tile_hi, uint32_t lo_delta, const float (&v)[4]) {
-        float4 hi, lo;
-        hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u); lo.x = v[0] - hi.x;
-        hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u); lo.y = v[1] - hi.y;
-        hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u); lo.z = v[2] - hi.z;
-        hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u); lo.w = v[3] - hi.w;
-        *reinterpret_cast<float4 *>(tile_hi) = hi;
-        *reinterpret_cast<float4 *>(tile_hi + lo_delta) = lo;
+        for (int i = 0; i < XR; ++i) xv[i] = ((xmask >> i) & 1) ? (kx ? __ldg(x + (size_t)i * 8 * ni) : fill) : 0.f;
     };
     load_chunk(0);
     for (int c = 0; c < n_chunks; ++c) {
@@ -162,9 +133,17 @@ mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, co
         // the MMAs that read this stage two chunks ago must have completed
         if (c >= 2) mbar_wait(bar0 + 8 * st, ((c >> 1) - 1) & 1);
 #pragma unroll
-        for (int i = 0; i < WI; ++i) split_store(stage + woff[i], TILE_A, wv[i]);
+        for (int i = 0; i < WR; ++i) {
+            const float v = wv[i], hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            *reinterpret_cast<float *>(stage + a_off + i * SBO) = hi;
+            *reinterpret_cast<float *>(stage + a_off + i * SBO + TILE_A) = v - hi;
+        }
 #pragma unroll
-        for (int i = 0; i < XI; ++i) split_store(stage + xoff[i], TILE_B, xv[i]);
+        for (int i = 0; i < XR; ++i) {
+            const float v = xv[i], hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            *reinterpret_cast<float *>(stage + b_off + i * SBO) = hi;
+            *reinterpret_cast<float *>(stage + b_off + i * SBO + TILE_B) = v - hi;
+        }
         if (c + 1 < n_chunks) load_chunk(c + 1);           // in flight across the barrier, the MMA issue and the next wait
         // generic-proxy stores -> visible to the tensor core's async proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

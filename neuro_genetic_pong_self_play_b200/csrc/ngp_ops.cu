@@ -210,6 +210,45 @@ __global__ void __launch_bounds__(256) mlp_layer_kernel(const float *__restrict_
         }
 }
 
+// last layer with few outputs (the action layer): one warp per (genome, env) row, lanes stride over k, FP64
+// accumulation, decision on the FP64 sigmoids (reference argmax incl. the saturation tie rule)
+__global__ void __launch_bounds__(256) mlp_last_small_kernel(const float *__restrict__ genomes, size_t w_off, int G, const float *__restrict__ in,
+                                                             int envs, int ni, int no, int bias, uint8_t *__restrict__ act, float *__restrict__ out)
+{
+    extern __shared__ float w_s[];                     // [no][ni + bias]
+    const int g = blockIdx.y, K = ni + bias;
+    const float *W = genomes + (size_t)g * G + w_off;
+    for (int i = threadIdx.x; i < no * K; i += blockDim.x) w_s[i] = __ldg(&W[i]);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (e >= envs) return;
+    const float *a = in + ((size_t)g * envs + e) * ni;
+    double z[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) z[o] = 0.0;
+    for (int k = lane; k < K; k += 32) {
+        const double x = k < ni ? (double)__ldg(&a[k]) : 1.0;
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+            if (o < no) z[o] += (double)w_s[o * K + k] * x;
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+        for (int off = 16; off; off >>= 1) z[o] += __shfl_down_sync(0xFFFFFFFFu, z[o], off);
+    if (lane == 0) {
+        int best = 0;
+        double sbest = 0.0;
+        const size_t row = (size_t)g * envs + e;
+        for (int o = 0; o < no; ++o) {
+            const double s = pol::det_sigmoid(z[o]);
+            if (out) out[row * no + o] = (float)s;
+            if (o == 0 || s > sbest) { sbest = s; best = o; }
+        }
+        act[row] = best == 0 ? pol::ACT_UP : pol::ACT_DOWN;
+    }
+}
+
 __global__ void mlp_decide_kernel(const double *__restrict__ z, long long rows, int n_out, uint8_t *__restrict__ act, float *__restrict__ out)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -267,6 +306,14 @@ extern "C" int ngp_mlp_forward(ngp_handle *h, const float *genomes, const float 
         const int ni = sh.nodes[l], no = sh.nodes[l + 1];
         dim3 grid((no + 63) / 64, (envs + 63) / 64, n_genomes);
         bool launched = false;
+        if (l == L - 1 && no <= 8 && (size_t)no * (ni + bias) * 4 <= 48 * 1024) {
+            // action layer: warp-per-row dot products, decision fused (no intermediate buffer)
+            dim3 g2((envs + 7) / 8, n_genomes);
+            mlp_last_small_kernel<<<g2, 256, (size_t)no * (ni + bias) * 4, st>>>(genomes, w_off, h->gene_size, in, envs, ni, no, bias, act, out);
+            h->launches++;
+            NGP_CUDA(cudaGetLastError());
+            return NGP_OK;
+        }
         if (l != L - 1 && !getenv("NGP_MLP_NO_TF32")) {
             // wide hidden layer with enough environments per genome: tensor cores (3xTF32, tcgen05 + TMEM)
             const int rc = ngp_mlp_layer_tf32(h, genomes, w_off, in, n_genomes, envs, ni, no, bias, bufs[l & 1], st);
