@@ -115,8 +115,10 @@ mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, co
     for (int i = 0; i < WR; ++i) wmask |= (o0 + warp + 8 * i < no ? 1u : 0u) << i;
 #pragma unroll
     for (int i = 0; i < XR; ++i) xmask |= (e0 + warp + 8 * i < envs ? 1u : 0u) << i;
-    float wv[WR], xv[XR];
-    auto load_chunk = [&](int c) {
+    // two chunks of loads (2 x 24 registers per thread = 48 KB per CTA) are kept in flight ahead of the stores: with ~1 us of
+    // HBM latency under load it takes ~45 KB in flight per SM to stream at full bandwidth
+    float wv0[WR], xv0[XR], wv1[WR], xv1[XR];
+    auto load_chunk = [&](int c, float (&wv)[WR], float (&xv)[XR]) {
         const int k = c * KC + lane;
         const bool kw = k < K, kx = k < ni;
         const float fill = (k == ni && bias) ? 1.0f : 0.0f;  // bias input column / zero padding
@@ -126,8 +128,7 @@ mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, co
 #pragma unroll
         for (int i = 0; i < XR; ++i) xv[i] = ((xmask >> i) & 1) ? (kx ? __ldg(x + (size_t)i * 8 * ni) : fill) : 0.f;
     };
-    load_chunk(0);
-    for (int c = 0; c < n_chunks; ++c) {
+    auto consume_chunk = [&](int c, float (&wv)[WR], float (&xv)[XR]) {
         const int st = c & 1;
         uint8_t *stage = smem + st * STAGE;
         // the MMAs that read this stage two chunks ago must have completed
@@ -144,7 +145,7 @@ mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, co
             *reinterpret_cast<float *>(stage + b_off + i * SBO) = hi;
             *reinterpret_cast<float *>(stage + b_off + i * SBO + TILE_B) = v - hi;
         }
-        if (c + 1 < n_chunks) load_chunk(c + 1);           // in flight across the barrier, the MMA issue and the next wait
+        if (c + 2 < n_chunks) load_chunk(c + 2, wv, xv);    // refill these registers two chunks ahead
         // generic-proxy stores -> visible to the tensor core's async proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -162,6 +163,12 @@ mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, co
             umma_commit(bar0 + 8 * st);                     // stage reusable when these MMAs are done
             if (c == n_chunks - 1) umma_commit(bar_done);   // accumulator complete
         }
+    };
+    load_chunk(0, wv0, xv0);
+    if (n_chunks > 1) load_chunk(1, wv1, xv1);
+    for (int c = 0; c < n_chunks; c += 2) {
+        consume_chunk(c, wv0, xv0);
+        if (c + 1 < n_chunks) consume_chunk(c + 1, wv1, xv1);
     }
     // ---- epilogue: TMEM -> registers -> sigmoid -> out[e][o] ----
     mbar_wait(bar_done, 0);
