@@ -118,15 +118,25 @@ mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, co
     // two chunks of loads (2 x 24 registers per thread = 48 KB per CTA) are kept in flight ahead of the stores: with ~1 us of
     // HBM latency under load it takes ~45 KB in flight per SM to stream at full bandwidth
     float wv0[WR], xv0[XR], wv1[WR], xv1[XR];
+    // interior chunks of full tiles need no predicates at all (the common case: 512 outputs, 64 environments)
+    const bool full_tile = (o0 + TM <= no) && (e0 + TN <= envs);
+    const size_t wstride = (size_t)8 * K, xstride = (size_t)8 * ni;
     auto load_chunk = [&](int c, float (&wv)[WR], float (&xv)[XR]) {
         const int k = c * KC + lane;
+        const float *w = wp + c * KC, *x = xp + c * KC;
+        if (full_tile && (c + 1) * KC <= ni) {
+#pragma unroll
+            for (int i = 0; i < WR; ++i) { wv[i] = __ldg(w); w += wstride; }
+#pragma unroll
+            for (int i = 0; i < XR; ++i) { xv[i] = __ldg(x); x += xstride; }
+            return;
+        }
         const bool kw = k < K, kx = k < ni;
         const float fill = (k == ni && bias) ? 1.0f : 0.0f;  // bias input column / zero padding
-        const float *w = wp + c * KC, *x = xp + c * KC;
 #pragma unroll
-        for (int i = 0; i < WR; ++i) wv[i] = (kw && ((wmask >> i) & 1)) ? __ldg(w + (size_t)i * 8 * K) : 0.f;
+        for (int i = 0; i < WR; ++i) wv[i] = (kw && ((wmask >> i) & 1)) ? __ldg(w + (size_t)i * wstride) : 0.f;
 #pragma unroll
-        for (int i = 0; i < XR; ++i) xv[i] = ((xmask >> i) & 1) ? (kx ? __ldg(x + (size_t)i * 8 * ni) : fill) : 0.f;
+        for (int i = 0; i < XR; ++i) xv[i] = ((xmask >> i) & 1) ? (kx ? __ldg(x + (size_t)i * xstride) : fill) : 0.f;
     };
     auto consume_chunk = [&](int c, float (&wv)[WR], float (&xv)[XR]) {
         const int st = c & 1;
@@ -190,10 +200,13 @@ mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, co
                 : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (o < no) {
+                // sigmoid with the fast exponential (ex2.approx, ~2 ulp) and an IEEE reciprocal: far inside the 1e-5 bar
+                float *dst = out + ((size_t)g * envs + e0 + half * 32) * no + o;
+                const int e_left = envs - (e0 + half * 32);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int e = e0 + half * 32 + j;
-                    if (e < envs) out[((size_t)g * envs + e) * no + o] = 1.0f / (1.0f + expf(-__uint_as_float(v[j])));
+                    if (j < e_left) *dst = __frcp_rn(1.0f + __expf(-__uint_as_float(v[j])));
+                    dst += no;
                 }
             }
         }

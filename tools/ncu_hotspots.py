@@ -28,10 +28,11 @@ def main():
     global CSRC
     if "--src" in sys.argv:      # csrc directory of the profiled source (e.g. from `git archive <commit>`)
         CSRC = sys.argv[sys.argv.index("--src") + 1]
+    tu = sys.argv[sys.argv.index("--tu") + 1] if "--tu" in sys.argv else "ngp_core.cu"
     tmp = tempfile.mkdtemp()
     cubin = os.path.join(tmp, "core.cubin")
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-cubin", "-o", cubin,
-                           os.path.join(CSRC, "ngp_core.cu")], stderr=subprocess.DEVNULL)
+                           os.path.join(CSRC, tu)], stderr=subprocess.DEVNULL)
     sass = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.split("\n")
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
