@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--population", type=int, default=POPULATION_PER_GPU, help="genomes per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-saturated", action="store_true", help="skip the saturated-GPU context measurement")
     return ap.parse_args()
 
 
@@ -279,6 +280,24 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        if world == 1 and not args.no_saturated:
+            # context, outside the timed region: the same kernel with enough environments to fill the GPU
+            # (population 16384 -> 98 304 environments).  The named workload above occupies ~2 % of the warp slots.
+            try:
+                n2 = 16384
+                eng2 = ngp.Engine(ngp.Config(SCHEDULE=ngp.SCHEDULE_ROUND_ROBIN, POPULATION_SIZE=n2, GAMES_TO_PLAY=GAMES), device=local)
+                g2 = eng2.init_population(n2, seed=77)
+                for _ in range(2):
+                    eng2.evaluate(g2, seed=5)
+                eng2.profile_enable(True); eng2.profile_read()
+                o2 = eng2.evaluate(g2, seed=6)
+                ms2, _ = eng2.profile_read()
+                line["saturated"] = {"workload": f"population {n2} round-robin, {n2 * GAMES} envs, 1 generation, full episodes",
+                                     "env_frames_per_s": o2["frames_total"] / (ms2 * 1e-3), "kernel_ms": ms2,
+                                     "issue_frac": (o2["frames_total"] * tipf / (ms2 * 1e-3) / issue_peak) if tipf else None}
+                eng2.close()
+            except Exception as e:  # never lose the headline line over the context measurement
+                line["saturated"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
