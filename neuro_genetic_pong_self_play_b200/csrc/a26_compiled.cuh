@@ -9,10 +9,19 @@
 // raises ERR_UNTRANSLATED (never happens for this cartridge: the traversal covers all of its code).
 #pragma once
 #include "a26_core.cuh"
+#include "pong_superblocks.cuh"
 
 namespace a26 {
 
 enum : int { ERR_UNTRANSLATED = 4 };
+
+// hook emitted by the generator at the head of dispatch entry $F621 (pong_superblocks.cuh)
+#ifndef A26_NO_SUPERBLOCKS
+#define A26_SUPERBLOCK_F621 \
+    if (superblock_f621<VERIFY>(s, T, ram, fb, a, x, y, sp, pc, fc, fv, nv, zv, fid, cyc, cpu_ls)) { A26_STAT(6); goto a26_next_; }
+#else
+#define A26_SUPERBLOCK_F621
+#endif
 
 #define A26_COMPILED_BLOCKMAP
 #include "generated/pong_core.inc"

@@ -22,10 +22,13 @@
 #ifdef A26_STATS
 extern unsigned long long a26_stats[16];
 extern unsigned long long a26_entry_stats[2048];
+extern unsigned long long a26_reg_stats[64];
+#define A26_STAT_REG(r) (++a26_reg_stats[(r) & 63])
 #define A26_STAT(i) (++a26_stats[i])
 #define A26_STAT_ENTRY(pc) (++a26_entry_stats[(pc) & 0x7FF])
 #else
 #define A26_STAT(i) ((void)0)
+#define A26_STAT_REG(r) ((void)0)
 #define A26_STAT_ENTRY(pc) ((void)0)
 #endif
 
@@ -188,6 +191,8 @@ struct Ram {
     {
         reinterpret_cast<uint8_t *>(base)[((a & 0x7C) << 5) | (a & 3)] = (uint8_t)v;
     }
+    // the aligned word holding byte a (little-endian: byte a&3 of the result)
+    __device__ __forceinline__ uint32_t rd32(uint32_t a) const { return base[(a & 0x7C) << 3]; }
 };
 
 // ---- 160-bit mask helpers ----------------------------------------------------------------------
@@ -618,6 +623,7 @@ template <bool VERIFY>
 __device__ __forceinline__ void tia_apply(Chip &s, const Tables &T, uint32_t reg, uint32_t v, uint32_t cyc_after, uint32_t cil, uint8_t *fb)
 {
     A26_STAT(1);
+    A26_STAT_REG(reg);
     const int hpos = 3 * (int)cil;
     int delay = 0;
     switch (reg) {
@@ -829,6 +835,7 @@ __device__ __forceinline__ void run_frame(Chip &s, CpuRegs &r, const Tables &T, 
         const uint32_t line_end = cpu_ls + LINE_CYCLES;
         while ((int32_t)(cyc - line_end) < 0 && !s.frame_done && !s.error) {
             if (!(pc & 0x1000)) { s.error = ERR_PC_NOT_ROM; break; }
+            A26_STAT_ENTRY(pc);
             // fetch 4 bytes at pc (wraps inside the 2 KiB image)
             const uint32_t pa = pc & 0x7FF;
             const uint32_t w0 = T.rom[pa >> 2], w1 = T.rom[((pa >> 2) + 1) & 511];

@@ -1,0 +1,129 @@
+// pong_superblocks.cuh -- hand-fused super-blocks of the bundled cartridge's hottest loops.
+//
+// The statically translated core (generated/pong_core.inc) spends ~65 % of a frame in the main display
+// loop $F5E0-$F63C: 91 iterations per frame, 48 instructions and two scanlines each, from one WSYNC to
+// the next.  One iteration is a pure function of X, eleven RAM cells and two paddle-capacitor reads; its
+// effects are eight TIA latch writes, two conditional RAM stores and the registers it leaves behind.
+// `superblock_f621` computes exactly that in one straight-line block: same values, same write order, same
+// CPU cycle stamp on every write and read, no flag bookkeeping for results nobody reads.  The TIA sees the
+// same (register, value, cycle) sequence as from the instruction-by-instruction translation, through the same
+// poke_quick / tia_poke functions.
+//
+// tools/gen_rom_core.py only emits the hook when the cartridge bytes of the loop are the ones this code
+// was written against; the guards at the top fall back to the generic translation for any state the
+// fused form does not cover (it never happens in this cartridge's own control flow).
+#pragma once
+#include "a26_core.cuh"
+
+namespace a26 {
+#ifdef __CUDACC__
+
+// SBC with carry set (the loop always executes SEC first), binary mode: result byte, carry, overflow
+__device__ __forceinline__ void sb_sbc(uint32_t acc, uint32_t m, uint32_t &r, uint32_t &c, uint32_t &v)
+{
+    const uint32_t m2 = m ^ 0xFFu;
+    const uint32_t sum = acc + m2 + 1u;
+    v = ((~(acc ^ m2) & (acc ^ sum)) >> 7) & 1u;
+    c = sum >> 8;
+    r = sum & 0xFFu;
+}
+// the byte PHP pushes: N and Z from `r`, C and V as given
+__device__ __forceinline__ uint32_t sb_php(uint32_t r, uint32_t c, uint32_t v, uint32_t fid)
+{
+    return c | ((r == 0u ? 1u : 0u) << 1) | fid | 0x30u | (v << 6) | (r & 0x80u);
+}
+
+// The display loop, entered at $F621 (the instruction after `STX WSYNC`); one iteration is
+//   $F621-$F63C  second line of the pair: GRP0, ENAM1, both paddle reads (INPTx bit 7 = capacitor charged; the data bus
+//                holds the operand high byte 0 before the read, so the low bits read 0), loop test
+//   $F5E0-$F61F  first line of the next pair: ENAM0, GRP1, PF0-2, GRP0 value, ENABL, STX WSYNC
+// Iterations run back to back until the loop test ends the loop (all lanes of a warp are in this loop during the same
+// scanlines: every frame of the cartridge has the same line structure).
+// Returns false (nothing touched) when a guard fails; otherwise pc is $F63E (loop ended) or $F621.
+template <bool VERIFY>
+__device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ram, uint8_t *fb, uint32_t &a, uint32_t &x, uint32_t &y,
+                                                uint32_t &sp, uint32_t &pc, uint32_t &fc, uint32_t &fv, uint32_t &nv, uint32_t &zv,
+                                                uint32_t fid, uint32_t &cyc, uint32_t cpu_ls)
+{
+#define A26_SB_POKE(REG_, V_, T_)                                                                              \
+    do {                                                                                                       \
+        const uint32_t pv_ = (V_);                                                                             \
+        if (!poke_quick(s, (REG_), pv_)) tia_poke<VERIFY>(s, T, (REG_), pv_, (T_), cpu_ls, fb);                \
+    } while (0)
+    if (sp != 0x1Eu || (fid & 8u)) return false;
+    // RAM cells the loop only reads (it writes $84/$85 and, through the stack pointer, TIA latches): loaded once
+    const uint32_t w80 = ram.rd32(0x80), wb0 = ram.rd32(0xB0), wb4 = ram.rd32(0xB4), wa4 = ram.rd32(0xA4), wa8 = ram.rd32(0xA8);
+    const uint32_t w98 = ram.rd32(0x98), w9c = ram.rd32(0x9C), wa0 = ram.rd32(0xA0);
+    const uint32_t sel = w80 & 0xFFu;                                   // $80: which paddle pair this frame reads
+    const uint32_t p0 = (w98 >> 24) | ((w9c & 0xFFu) << 8), p1 = (w9c >> 8) & 0xFFFFu, p2 = (w9c >> 24) | ((wa0 & 0xFFu) << 8);
+    // playfield rows are read from ROM for every Y the loop can produce (Y = X >> 3 < 32)
+    if (sel >= 2u || !(p0 & p1 & p2 & (p0 + 31u) & (p1 + 31u) & (p2 + 31u) & 0x1000u)) return false;
+    const uint32_t b2 = (wb0 >> 16) & 0xFFu, b3 = wb0 >> 24, b4 = wb4 & 0xFFu, b5 = (wb4 >> 8) & 0xFFu, b6 = (wb4 >> 16) & 0xFFu;
+    const uint32_t a5 = (wa4 >> 8) & 0xFFu, a6 = (wa4 >> 16) & 0xFFu, a7 = wa4 >> 24, a8 = wa8 & 0xFFu;
+    // paddle capacitors: dump state and thresholds only change in VBLANK code
+    const bool dumped = s.dump_enabled != 0;
+    const uint32_t dump_cyc = s.dump_cyc, need0 = s.needed[sel], need1 = s.needed[2u + sel];
+    // bounded: at most one trip of X through its 8-bit range per call, then back through the dispatcher
+    for (int iter = 0; iter < 128; ++iter) {
+        const uint32_t x1 = (x + 1u) & 0xFFu, x2 = (x + 2u) & 0xFFu;
+        const uint32_t row = x1 >> 3;                                   // TXA, LSR x3, TAY
+        const uint32_t t0 = cyc;
+        uint32_t r, c, v;
+
+        // ---- $F621 STY GRP0 ; TXA ; SEC ; SBC $B5 ; AND $A8 ; PHP (sp=$1E -> ENAM1) ----
+        A26_SB_POKE(0x1Bu, y, t0 + 3u);
+        sb_sbc(x, b5, r, c, v);
+        r &= a8;
+        A26_SB_POKE(0x1Eu, sb_php(r, c, v, fid), t0 + 16u);
+        // ---- LDY $80 ; LDA $0038,Y ; BMI ; STX $84 ; LDA $003A,Y ; BMI ; STX $85 ----
+        uint32_t k = 23u;
+        const uint32_t in0 = (!dumped && (t0 + k - dump_cyc) > need0) ? 0x80u : 0u;
+        if (in0) k += 3u; else { ram.wr(0x84u, x); k += 5u; }
+        k += 4u;
+        const uint32_t in1 = (!dumped && (t0 + k - dump_cyc) > need1) ? 0x80u : 0u;
+        if (in1) k += 3u; else { ram.wr(0x85u, x); k += 5u; }
+        // ---- CPX #$DC ; BNE $F5E0 ----
+        if (x == 0xDCu) {
+            a = in1; y = sel; sp = 0x1Du; fc = 1u; fv = v; nv = zv = 0u;
+            cyc = t0 + k + 4u; pc = 0xF63Eu;
+            return true;
+        }
+        k += 6u;                                                        // CPX 2 + taken branch across a page 4
+        // ---- $F5E0 TXA ; LDY #$F0 ; SEC ; SBC $B3 ; AND $A6 ; BEQ ; LDY #$00 ----
+        const uint32_t g1 = (((x - b3) & a6) & 0xFFu) == 0u ? 0xF0u : 0x00u;
+        k += 12u + (g1 ? 3u : 4u);
+        // ---- TXA ; INX ; SEC ; SBC $B4 ; AND $A7 ; PHP (sp=$1D -> ENAM0) ; STY GRP1 ----
+        sb_sbc(x, b4, r, c, v);
+        r &= a7;
+        k += 15u;
+        A26_SB_POKE(0x1Du, sb_php(r, c, v, fid), t0 + k);
+        k += 3u;
+        A26_SB_POKE(0x1Cu, g1, t0 + k);
+        // ---- TXA ; LSR ; LSR ; LSR ; TAY ; LDA ($9B),Y ; STA PF0 ; LDA ($9D),Y ; STA PF1 ; LDA ($9F),Y ; STA PF2 ----
+        k += 10u;
+        k += 8u + (((p0 & 0xFFu) + row) >> 8);
+        A26_SB_POKE(0x0Du, rom_byte(T, p0 + row), t0 + k);
+        k += 8u + (((p1 & 0xFFu) + row) >> 8);
+        A26_SB_POKE(0x0Eu, rom_byte(T, p1 + row), t0 + k);
+        k += 8u + (((p2 & 0xFFu) + row) >> 8);
+        A26_SB_POKE(0x0Fu, rom_byte(T, p2 + row), t0 + k);
+        // ---- INX ; TXA ; LDX #$1F ; TXS ; TAX ; LDY #$F0 ; SEC ; SBC $B2 ; AND $A5 ; BEQ ; LDY #$00 ----
+        const uint32_t g0 = (((x2 - b2) & a5) & 0xFFu) == 0u ? 0xF0u : 0x00u;
+        k += 20u + (g0 ? 3u : 4u);
+        // ---- TXA ; SEC ; SBC $B6 ; AND #$FC ; PHP (sp=$1F -> ENABL) ; STX WSYNC ----
+        sb_sbc(x2, b6, r, c, v);
+        r &= 0xFCu;
+        k += 12u;
+        A26_SB_POKE(0x1Fu, sb_php(r, c, v, fid), t0 + k);
+        k += 3u;
+        a = r; x = x2; y = g0; fc = c; fv = v; nv = zv = r;
+        cyc = t0 + k;
+        cyc += wsync_stall(cyc, cpu_ls);
+    }
+    pc = 0xF621u;
+    return true;
+#undef A26_SB_POKE
+}
+
+#endif  // __CUDACC__
+}  // namespace a26

@@ -11,6 +11,7 @@ bit-for-bit against the CPU oracle.
 
 Usage: python tools/gen_rom_core.py        (rewrites the .inc next to the other CUDA sources)
 """
+import hashlib
 import os
 import re
 import sys
@@ -32,6 +33,10 @@ PAGE_PENALTY = {"abx", "aby", "izy"}          # only for read instructions
 MAX_STRUCTURED_SKIP = 24                      # bytes a structured forward branch may skip
 # dispatch entries tried first, hottest first (dispatches per frame measured with tests/host_sim + A26_STATS)
 HOT_ENTRIES = [0xF621, 0xF58D, 0xF58B, 0xF5CC, 0xF5B8, 0xF21F, 0xF094]
+# Hand-fused super-blocks (csrc/pong_superblocks.cuh): dispatch entry -> (first byte, last byte + 1, sha1 of the cartridge
+# bytes the fused code was written against).  The hook is only emitted when the ROM still holds exactly those bytes.
+SUPERBLOCKS = {0xF621: (0xF5E0, 0xF63E, "9cf83bee22051baf07f26f6b6fd104e7b6f90ebe")}
+SUPERBLOCK_EXITS = [0xF63E]          # program counters a super-block can leave with: must be dispatch entries
 
 
 def load_rom():
@@ -100,6 +105,7 @@ def traverse(rom):
                 if static_ea is None or (addr_class(static_ea) == "tia" and (static_ea & 0x3F) in (0x00, 0x02)):
                     leaders.add(nxt)
             pc = nxt
+    leaders.update(a for a in SUPERBLOCK_EXITS if a in instrs)
     # every instruction start inside the jump-table area can be entered through the RAM vectors
     for a in instrs:
         if 0xF337 <= a <= 0xF41F:
@@ -440,6 +446,13 @@ class Gen:
                 if self.open_regions:
                     raise SystemExit(f"leader {pc:04X} inside a structured region")
                 self.out.append(f"case {ids[pc]}: @LABEL_{pc:04X}@ /* ---- {pc:04X} ---- */")
+                if pc in SUPERBLOCKS:
+                    lo, hi, want = SUPERBLOCKS[pc]
+                    got = hashlib.sha1(bytes(rb(self.rom, a) for a in range(lo, hi))).hexdigest()
+                    if got == want:
+                        self.out.append(f"  A26_SUPERBLOCK_{pc:04X}")
+                    else:
+                        print(f"note: super-block {pc:04X} not emitted (cartridge bytes {lo:04X}-{hi - 1:04X} hash {got})")
             elif not prev_fell_through:
                 # unreachable by fall-through and not a leader: cannot happen (every entry is a leader)
                 raise SystemExit(f"instruction {pc:04X} is neither a leader nor reached by fall-through")
