@@ -18,7 +18,7 @@ enum : int { ERR_UNTRANSLATED = 4 };
 // hook emitted by the generator at the head of dispatch entry $F621 (pong_superblocks.cuh)
 #ifndef A26_NO_SUPERBLOCKS
 #define A26_SUPERBLOCK_F621 \
-    if (superblock_f621<VERIFY>(s, T, ram, fb, a, x, y, sp, pc, fc, fv, nv, zv, fid, cyc, cpu_ls)) { A26_STAT(6); goto a26_next_; }
+    if (superblock_f621<VERIFY>(s, T, ram, fb, a, x, y, sp, pc, fc, fv, nv, zv, fid, cyc, cpu_ls, sb_iters)) { A26_STAT(6); goto a26_next_; }
 #else
 #define A26_SUPERBLOCK_F621
 #endif
@@ -83,6 +83,12 @@ __device__ __forceinline__ void run_frame_compiled(Chip &s, CpuRegs &r, const Ta
     }
     const uint32_t start_cyc = cyc;
     for (uint32_t slot = 0;; ++slot) {
+        // The display loop's super-block runs all of its iterations in one go only when every lane of the warp that is
+        // still inside its frame stands at the loop entry: environments in different game phases reach the loop a few
+        // slots apart, and a lane that ran ahead alone would execute the whole loop a second time for the others.
+        // (Only a scheduling hint: any iteration count gives the same machine state.)
+        const int sb_iters = __all_sync(__activemask(), done || pc == 0xF621u) ? 128 : 1;
+        (void)sb_iters;
         if (!done) {
             if ((cyc - start_cyc) >= FRAME_CYCLE_CAP) done = 1;
             else {

@@ -24,11 +24,13 @@ extern unsigned long long a26_stats[16];
 extern unsigned long long a26_entry_stats[2048];
 extern unsigned long long a26_reg_stats[64];
 #define A26_STAT_REG(r) (++a26_reg_stats[(r) & 63])
+#define A26_STAT_SLOT(sl) (++a26_entry_stats[(sl) & 0x7FF])
 #define A26_STAT(i) (++a26_stats[i])
 #define A26_STAT_ENTRY(pc) (++a26_entry_stats[(pc) & 0x7FF])
 #else
 #define A26_STAT(i) ((void)0)
 #define A26_STAT_REG(r) ((void)0)
+#define A26_STAT_SLOT(sl) ((void)0)
 #define A26_STAT_ENTRY(pc) ((void)0)
 #endif
 

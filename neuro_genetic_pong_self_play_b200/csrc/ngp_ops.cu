@@ -12,67 +12,101 @@
 // K2: find_stuff.  HBM-bound: 76 800 B of cropped RGB per frame, read once with 16-byte loads.
 // The crop [34,194) x 160 x 3 is one contiguous byte range of the frame; a 16-byte vector never
 // straddles a row (480 = 30 * 16), and its channel phase is (vector index mod 3).
+//
+// 192-thread CTAs (a multiple of 3): thread t always sees vectors of phase t % 3, so its twelve
+// comparison words (3 targets x 4 words) live in registers, and 4800 vectors per frame are exactly 25
+// per thread.  The stream path only asks "does any byte of this vector equal its target byte?" with
+// the exact zero-byte test ((z - 0x01010101) & ~z & 0x80808080 on z = data ^ pattern: 3 instructions per
+// word and target); the rare vectors that hold an object pixel (< 1 % of a frame) take the exact
+// per-byte accounting.  One redux.sync per accumulator and frame.
 // =================================================================================================
 struct FindStuffPatterns { uint32_t w[3][3][4]; };   // [phase][target][word]: target bytes repeated with the phase
 
-__global__ void __launch_bounds__(256) find_stuff_kernel(const uint8_t *__restrict__ frames, int n, FindStuffPatterns pat,
-                                                         float *__restrict__ loc, uint8_t *__restrict__ valid)
+constexpr int FS_THREADS = 192;
+constexpr int FS_VEC_PER_FRAME = (a26::CROP_BOTTOM - a26::CROP_TOP) * 480 / 16;   // 4800
+constexpr int FS_ROUNDS = FS_VEC_PER_FRAME / FS_THREADS;                           // 25
+static_assert(FS_ROUNDS * FS_THREADS == FS_VEC_PER_FRAME && FS_THREADS % 3 == 0, "find_stuff tiling");
+
+__device__ __forceinline__ uint32_t fs_zero_byte(uint32_t z) { return (z - 0x01010101u) & ~z & 0x80808080u; }
+
+// Exact accounting of one vector that contains at least one matching byte.  Sums are kept linear so that no per-byte
+// division is needed: a matching byte at offset B of its row with channel ch belongs to column (B - ch) / 3, so a target's
+// column sum is (sum of B - sum of ch) / 3, divided once per frame.  Per word: exact zero-byte mask, popcount, and the two
+// weighted byte sums as one multiply each (byte 3 of b * c is sum b_i * c_(3-i) for 0/1 bytes b_i).
+__device__ __forceinline__ void fs_account(uint32_t (&acc)[9], const uint32_t (&words)[4], const uint32_t (&pt)[3][4], int k, int phase)
 {
-    constexpr int VEC_PER_FRAME = (a26::CROP_BOTTOM - a26::CROP_TOP) * 480 / 16;   // 4800
-    __shared__ uint32_t red[8][9];
-    for (int f = blockIdx.x; f < n; f += gridDim.x) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(frames + (size_t)f * (a26::FB_ROWS * 480) + a26::CROP_TOP * 480);
+    const uint32_t row = (uint32_t)k / 30u, byte0 = ((uint32_t)k % 30u) * 16u;
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int wi = 0; wi < 4; ++wi) {
+            const uint32_t z = words[wi] ^ pt[t][wi];
+            if (!fs_zero_byte(z)) continue;
+            const uint32_t b = (~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & 0x80808080u) >> 7;     // 1 in every matching byte
+            const uint32_t c = __popc(b);
+            const uint32_t p0 = (uint32_t)(phase + wi) % 3u, p1 = (p0 + 1u) % 3u, p2 = (p0 + 2u) % 3u;   // channels of bytes 0,1,2 (3 = 0)
+            const uint32_t chc = p0 | (p2 << 8) | (p1 << 16) | (p0 << 24);
+            const uint32_t sidx = (b * 0x00010203u) >> 24, sch = (b * chc) >> 24;
+            acc[3 * t] += c; acc[3 * t + 1] += c * row; acc[3 * t + 2] += c * (byte0 + 4u * wi) + sidx - sch;
+        }
+}
+
+__global__ void __launch_bounds__(FS_THREADS) find_stuff_kernel(const uint8_t *__restrict__ frames, int n, FindStuffPatterns pat,
+                                                                float *__restrict__ loc, uint8_t *__restrict__ valid)
+{
+    __shared__ uint32_t red[2][FS_THREADS / 32][9];          // double-buffered: one barrier per frame
+    const int tid = threadIdx.x, phase = tid % 3;
+    uint32_t pt[3][4];
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int wi = 0; wi < 4; ++wi) pt[t][wi] = pat.w[phase][t][wi];
+    int buf = 0;
+    for (int f = blockIdx.x; f < n; f += gridDim.x, buf ^= 1) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(frames + (size_t)f * (a26::FB_ROWS * 480) + a26::CROP_TOP * 480) + tid;
         uint32_t acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};       // per target: count, sum row, sum col
-        // 4800 vectors per frame, 256 threads: 19 rounds; loads are issued four at a time before any compare so
-        // that each thread keeps 64 B in flight (the kernel is a pure HBM stream)
-        constexpr int ROUNDS = (VEC_PER_FRAME + 255) / 256;
 #pragma unroll 1
-        for (int r0 = 0; r0 < ROUNDS; r0 += 4) {
-            uint4 vec[4];
-            bool ok[4];
+        for (int r0 = 0; r0 < FS_ROUNDS; r0 += 5) {
+            uint4 vec[5];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = threadIdx.x + (r0 + j) * 256;
-                ok[j] = (r0 + j) < ROUNDS && k < VEC_PER_FRAME;
-                if (ok[j]) vec[j] = __ldcs(&src[k]);
-            }
+            for (int j = 0; j < 5; ++j) vec[j] = __ldcs(&src[(r0 + j) * FS_THREADS]);     // 80 B in flight per thread
+            uint32_t flagged = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (!ok[j]) continue;
-                const int k = threadIdx.x + (r0 + j) * 256;
+            for (int j = 0; j < 5; ++j) {
                 const uint32_t words[4] = {vec[j].x, vec[j].y, vec[j].z, vec[j].w};
-                const int phase = k % 3, row = k / 30, byte0 = (k % 30) * 16;
+                uint32_t any = 0;
 #pragma unroll
-                for (int t = 0; t < 3; ++t) {
+                for (int t = 0; t < 3; ++t)
 #pragma unroll
-                    for (int wi = 0; wi < 4; ++wi) {
-                        uint32_t m = __vcmpeq4(words[wi], pat.w[phase][t][wi]) & 0x01010101u;
-                        if (m) {
-                            const int b = byte0 + wi * 4;
-                            uint32_t c = __popc(m);
-                            uint32_t sc = (m & 1) * (b / 3) + ((m >> 8) & 1) * ((b + 1) / 3) + ((m >> 16) & 1) * ((b + 2) / 3) +
-                                          ((m >> 24) & 1) * ((b + 3) / 3);
-                            acc[3 * t] += c; acc[3 * t + 1] += c * row; acc[3 * t + 2] += sc;
-                        }
-                    }
+                    for (int wi = 0; wi < 4; ++wi) any |= fs_zero_byte(words[wi] ^ pt[t][wi]);
+                flagged |= (any ? 1u : 0u) << j;
+            }
+            // rare: a vector with an object pixel is fetched again (L2) and accounted for exactly; kept out of the unrolled
+            // stream so that the hot loop stays a few KB of straight-line code
+            if (flagged) {
+#pragma unroll 1
+                for (int j = 0; j < 5; ++j) {
+                    if (!((flagged >> j) & 1u)) continue;
+                    const uint4 v = src[(r0 + j) * FS_THREADS];
+                    const uint32_t words[4] = {v.x, v.y, v.z, v.w};
+                    fs_account(acc, words, pt, tid + (r0 + j) * FS_THREADS, phase);
                 }
             }
         }
 #pragma unroll
-        for (int i = 0; i < 9; ++i)
-            for (int off = 16; off; off >>= 1) acc[i] += __shfl_down_sync(0xFFFFFFFFu, acc[i], off);
-        if ((threadIdx.x & 31) == 0)
-            for (int i = 0; i < 9; ++i) red[threadIdx.x >> 5][i] = acc[i];
+        for (int i = 0; i < 9; ++i) acc[i] = __reduce_add_sync(0xFFFFFFFFu, acc[i]);
+        if ((tid & 31) == 0)
+#pragma unroll
+            for (int i = 0; i < 9; ++i) red[buf][tid >> 5][i] = acc[i];
         __syncthreads();
-        if (threadIdx.x < 3) {
-            const int t = threadIdx.x;
+        if (tid < 3) {
             uint32_t c = 0, sr = 0, sc = 0;
-            for (int w = 0; w < 8; ++w) { c += red[w][3 * t]; sr += red[w][3 * t + 1]; sc += red[w][3 * t + 2]; }
-            valid[f * 3 + t] = c > 0;
-            loc[(f * 3 + t) * 2 + 0] = c ? (float)((double)sr / (double)c) : 0.f;
-            loc[(f * 3 + t) * 2 + 1] = c ? (float)((double)sc / (double)c) : 0.f;
+#pragma unroll
+            for (int w = 0; w < FS_THREADS / 32; ++w) { c += red[buf][w][3 * tid]; sr += red[buf][w][3 * tid + 1]; sc += red[buf][w][3 * tid + 2]; }
+            valid[f * 3 + tid] = c > 0;
+            loc[(f * 3 + tid) * 2 + 0] = c ? (float)((double)sr / (double)c) : 0.f;
+            loc[(f * 3 + tid) * 2 + 1] = c ? (float)((double)(sc / 3u) / (double)c) : 0.f;
         }
-        __syncthreads();
     }
 }
 
@@ -90,8 +124,14 @@ extern "C" int ngp_find_stuff(ngp_handle *h, const uint8_t *frames, int32_t n, f
                 for (int j = 0; j < 4; ++j) v |= (uint32_t)targets[t][(phase + w * 4 + j) % 3] << (8 * j);
                 pat.w[phase][t][w] = v;
             }
-    int grid = n < h->sm_count * 8 ? n : h->sm_count * 8;
-    find_stuff_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, n, pat, loc, valid);
+    // persistent CTAs over frames, as many as are resident at once
+    static int per_sm = 0;
+    if (!per_sm) {
+        NGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, find_stuff_kernel, FS_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+    }
+    int grid = n < h->sm_count * per_sm ? n : h->sm_count * per_sm;
+    find_stuff_kernel<<<grid, FS_THREADS, 0, (cudaStream_t)stream>>>(frames, n, pat, loc, valid);
     h->launches++;
     NGP_CUDA(cudaGetLastError());
     return NGP_OK;
@@ -210,6 +250,40 @@ __global__ void __launch_bounds__(256) mlp_layer_kernel(const float *__restrict_
         }
 }
 
+// hidden layer with a tiny fan-in (the first layer: 6 observation values + bias) and a wide fan-out: write-bound.
+// Thread = one output unit with its weight row in registers, the genome's input rows in shared memory (broadcast
+// reads), stores coalesced along the outputs.  Same accumulation order as mlp_layer_kernel (k ascending, bias last).
+constexpr int NARROW_K = 8;
+__global__ void __launch_bounds__(128) mlp_narrow_in_kernel(const float *__restrict__ genomes, size_t w_off, int G, const float *__restrict__ in,
+                                                            int envs, int ni, int no, int bias, float *__restrict__ outp)
+{
+    constexpr int TE = 64;
+    __shared__ float xs[TE * NARROW_K];
+    const int g = blockIdx.z, e0 = blockIdx.y * TE, o = blockIdx.x * 128 + threadIdx.x;
+    const int K = ni + bias, ne = min(TE, envs - e0);
+    const float *src = in + ((size_t)g * envs + e0) * ni;
+    for (int i = threadIdx.x; i < ne * ni; i += 128) xs[i] = __ldg(&src[i]);
+    float w[NARROW_K];
+    const float *W = genomes + (size_t)g * G + w_off + (size_t)min(o, no - 1) * K;
+#pragma unroll
+    for (int k = 0; k < NARROW_K; ++k) w[k] = k < K ? __ldg(&W[k]) : 0.f;
+    float wb = 0.f;
+    if (bias) {
+#pragma unroll
+        for (int k = 0; k < NARROW_K; ++k) if (k == ni) { wb = w[k]; w[k] = 0.f; }
+    }
+    __syncthreads();
+    if (o >= no) return;
+    float *dst = outp + ((size_t)g * envs + e0) * no + o;
+    for (int e = 0; e < ne; ++e) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < NARROW_K; ++k) if (k < ni) acc = fmaf(xs[e * ni + k], w[k], acc);
+        if (bias) acc = fmaf(1.0f, wb, acc);
+        dst[(size_t)e * no] = sigmoid_f32(acc);
+    }
+}
+
 // last layer with few outputs (the action layer): one warp per (genome, env) row, lanes stride over k, FP64
 // accumulation, decision on the FP64 sigmoids (reference argmax incl. the saturation tie rule)
 __global__ void __launch_bounds__(256) mlp_last_small_kernel(const float *__restrict__ genomes, size_t w_off, int G, const float *__restrict__ in,
@@ -246,6 +320,73 @@ __global__ void __launch_bounds__(256) mlp_last_small_kernel(const float *__rest
             if (o == 0 || s > sbest) { sbest = s; best = o; }
         }
         act[row] = best == 0 ? pol::ACT_UP : pol::ACT_DOWN;
+    }
+}
+
+// Action layer on top of a wide hidden layer (fan-in a multiple of 128, up to 512; one or two outputs): CTA = one genome,
+// warp w owns environments w, w+8, ..  Each lane keeps its 16 k-positions of every weight row in FP64 registers (loaded once
+// per genome), streams the activation rows with 16-byte loads (two rows in flight) and accumulates in FP64; the decision
+// is taken on the FP64 sigmoids like mlp_last_small_kernel.
+template <int NO>
+__global__ void __launch_bounds__(256) mlp_last_wide_kernel(const float *__restrict__ genomes, size_t w_off, int G, const float *__restrict__ in,
+                                                            int envs, int ni, int bias, uint8_t *__restrict__ act, float *__restrict__ out)
+{
+    const int g = blockIdx.x, K = ni + bias, kj = ni >> 7;
+    const float *W = genomes + (size_t)g * G + w_off;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double w[NO][16];
+#pragma unroll
+    for (int o = 0; o < NO; ++o)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[o][4 * j + i] = j < kj ? (double)__ldg(&W[(size_t)o * K + 128 * j + 4 * lane + i]) : 0.0;
+    double wb[NO];
+#pragma unroll
+    for (int o = 0; o < NO; ++o) wb[o] = bias ? (double)__ldg(&W[(size_t)o * K + ni]) : 0.0;
+    for (int e = warp; e < envs; e += 16) {
+        const int e2 = e + 8;
+        const bool two = e2 < envs;
+        const float4 *a0 = reinterpret_cast<const float4 *>(in + ((size_t)g * envs + e) * ni) + lane;
+        const float4 *a1 = reinterpret_cast<const float4 *>(in + ((size_t)g * envs + (two ? e2 : e)) * ni) + lane;
+        float4 x0[4], x1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < kj) { x0[j] = __ldcs(&a0[32 * j]); x1[j] = __ldcs(&a1[32 * j]); }
+        double z0[NO], z1[NO];
+#pragma unroll
+        for (int o = 0; o < NO; ++o) { z0[o] = 0.0; z1[o] = 0.0; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j >= kj) continue;
+            const double d0[4] = {(double)x0[j].x, (double)x0[j].y, (double)x0[j].z, (double)x0[j].w};
+            const double d1[4] = {(double)x1[j].x, (double)x1[j].y, (double)x1[j].z, (double)x1[j].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int o = 0; o < NO; ++o) { z0[o] += w[o][4 * j + i] * d0[i]; z1[o] += w[o][4 * j + i] * d1[i]; }
+        }
+#pragma unroll
+        for (int o = 0; o < NO; ++o)
+            for (int off = 16; off; off >>= 1) {
+                z0[o] += __shfl_down_sync(0xFFFFFFFFu, z0[o], off);
+                z1[o] += __shfl_down_sync(0xFFFFFFFFu, z1[o], off);
+            }
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (r == 1 && !two) break;
+                const size_t row = (size_t)g * envs + (r ? e2 : e);
+                int best = 0;
+                double sbest = 0.0;
+#pragma unroll
+                for (int o = 0; o < NO; ++o) {
+                    const double sg = pol::det_sigmoid((r ? z1[o] : z0[o]) + wb[o]);
+                    if (out) out[row * NO + o] = (float)sg;
+                    if (o == 0 || sg > sbest) { sbest = sg; best = o; }
+                }
+                act[row] = best == 0 ? pol::ACT_UP : pol::ACT_DOWN;
+            }
+        }
     }
 }
 
@@ -308,13 +449,27 @@ extern "C" int ngp_mlp_forward(ngp_handle *h, const float *genomes, const float 
         bool launched = false;
         if (l == L - 1 && no <= 8 && (size_t)no * (ni + bias) * 4 <= 48 * 1024) {
             // action layer: warp-per-row dot products, decision fused (no intermediate buffer)
+            if (no <= 2 && ni % 128 == 0 && ni <= 512 && l > 0) {      // on top of a wide hidden layer (our own 16-byte aligned scratch)
+                if (no == 2) mlp_last_wide_kernel<2><<<n_genomes, 256, 0, st>>>(genomes, w_off, h->gene_size, in, envs, ni, bias, act, out);
+                else mlp_last_wide_kernel<1><<<n_genomes, 256, 0, st>>>(genomes, w_off, h->gene_size, in, envs, ni, bias, act, out);
+                h->launches++;
+                NGP_CUDA(cudaGetLastError());
+                return NGP_OK;
+            }
             dim3 g2((envs + 7) / 8, n_genomes);
             mlp_last_small_kernel<<<g2, 256, (size_t)no * (ni + bias) * 4, st>>>(genomes, w_off, h->gene_size, in, envs, ni, no, bias, act, out);
             h->launches++;
             NGP_CUDA(cudaGetLastError());
             return NGP_OK;
         }
-        if (l != L - 1 && !getenv("NGP_MLP_NO_TF32")) {
+        if (l != L - 1 && ni + bias <= NARROW_K) {
+            dim3 g3((no + 127) / 128, (envs + 63) / 64, n_genomes);
+            mlp_narrow_in_kernel<<<g3, 128, 0, st>>>(genomes, w_off, h->gene_size, in, envs, ni, no, bias, bufs[l & 1]);
+            h->launches++;
+            NGP_CUDA(cudaGetLastError());
+            launched = true;
+        }
+        if (!launched && l != L - 1 && !getenv("NGP_MLP_NO_TF32")) {
             // wide hidden layer with enough environments per genome: tensor cores (3xTF32, tcgen05 + TMEM)
             const int rc = ngp_mlp_layer_tf32(h, genomes, w_off, in, n_genomes, envs, ni, no, bias, bufs[l & 1], st);
             if (rc == NGP_OK) launched = true;

@@ -37,13 +37,12 @@ __device__ __forceinline__ uint32_t sb_php(uint32_t r, uint32_t c, uint32_t v, u
 //   $F621-$F63C  second line of the pair: GRP0, ENAM1, both paddle reads (INPTx bit 7 = capacitor charged; the data bus
 //                holds the operand high byte 0 before the read, so the low bits read 0), loop test
 //   $F5E0-$F61F  first line of the next pair: ENAM0, GRP1, PF0-2, GRP0 value, ENABL, STX WSYNC
-// Iterations run back to back until the loop test ends the loop (all lanes of a warp are in this loop during the same
-// scanlines: every frame of the cartridge has the same line structure).
+// Up to max_iters iterations run back to back, until the loop test ends the loop.
 // Returns false (nothing touched) when a guard fails; otherwise pc is $F63E (loop ended) or $F621.
 template <bool VERIFY>
 __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ram, uint8_t *fb, uint32_t &a, uint32_t &x, uint32_t &y,
                                                 uint32_t &sp, uint32_t &pc, uint32_t &fc, uint32_t &fv, uint32_t &nv, uint32_t &zv,
-                                                uint32_t fid, uint32_t &cyc, uint32_t cpu_ls)
+                                                uint32_t fid, uint32_t &cyc, uint32_t cpu_ls, int max_iters)
 {
 #define A26_SB_POKE(REG_, V_, T_)                                                                              \
     do {                                                                                                       \
@@ -63,8 +62,8 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
     // paddle capacitors: dump state and thresholds only change in VBLANK code
     const bool dumped = s.dump_enabled != 0;
     const uint32_t dump_cyc = s.dump_cyc, need0 = s.needed[sel], need1 = s.needed[2u + sel];
-    // bounded: at most one trip of X through its 8-bit range per call, then back through the dispatcher
-    for (int iter = 0; iter < 128; ++iter) {
+    // bounded by the caller (at most one trip of X through its 8-bit range), then back through the dispatcher
+    for (int iter = 0; iter < max_iters; ++iter) {
         const uint32_t x1 = (x + 1u) & 0xFFu, x2 = (x + 2u) & 0xFFu;
         const uint32_t row = x1 >> 3;                                   // TXA, LSR x3, TAY
         const uint32_t t0 = cyc;

@@ -36,6 +36,8 @@ static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline void __syncthreads() {}
+static inline unsigned __activemask() { return 1u; }
+static inline int __all_sync(unsigned, int v) { return v; }
 static inline int __syncthreads_or(int v) { return v; }
 
 #include "../../neuro_genetic_pong_self_play_b200/csrc/rollout.cuh"

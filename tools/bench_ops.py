@@ -51,16 +51,17 @@ def synth_frames(n, seed=0):
 
 
 def main():
+    only = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else ["find_stuff", "mlp_small", "mlp_wide", "ga"]
     eng = ngp.Engine(ngp.Config(), device=0)
     # K2: frames larger than L2 (126 MB): 4096 frames = 413 MB
     base = torch.from_numpy(synth_frames(64)).cuda()
-    for n in (1024, 4096, 16384):
+    for n in (1024, 4096, 16384) if "find_stuff" in only else ():
         frames = base.repeat(n // 64, 1, 1, 1).contiguous()
         t = timed(lambda: eng.find_stuff(frames))
         report("find_stuff", {"frames": n, "bytes_per_frame": 76800 + 27}, t, n * (76800 + 27), n, "frames")
         del frames
     # K3 default net: one env per genome, HBM-bound on genomes + inputs + outputs
-    for logn in (10, 14, 17, 20):
+    for logn in (10, 14, 17, 20) if "mlp_small" in only else ():
         n = 1 << logn
         g = eng.init_population(n, seed=1)
         x = torch.rand((n, 1, 6), device="cuda")
@@ -69,7 +70,7 @@ def main():
     # K3 wide net, 64 envs per genome: weights streamed once per genome
     engw = ngp.Engine(ngp.Config(NETWORK_SHAPE=(6, 512, 512, 2)), device=0)
     G = engw.gene_size
-    for n in (64, 256, 1024):
+    for n in (64, 256, 1024) if "mlp_wide" in only else ():
         g = (torch.randn((n, G), device="cuda") * 0.05)
         x = torch.rand((n, 64, 6), device="cuda")
         for path in ("tcgen05_3xtf32", "fp32_ffma"):
@@ -83,7 +84,7 @@ def main():
                               "frac": n * G * 4 / t / 1e9 / PEAK, "tflops_algorithmic": flops / t / 1e12}), flush=True)
     engw.close()
     # K4: GA step, ~3*N*G*4 bytes
-    for logn in (10, 14, 17):
+    for logn in (10, 14, 17) if "ga" in only else ():
         n = 1 << logn
         e = ngp.Engine(ngp.Config(POPULATION_SIZE=n), device=0)
         g = e.init_population(n, seed=2)
