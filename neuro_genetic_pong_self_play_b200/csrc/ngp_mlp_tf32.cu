@@ -17,8 +17,9 @@
 // ridge of ~170 flop/B), so the split costs no time.
 // Pipeline: K is walked in chunks of 32 floats through two shared-memory stages.  All 256 threads load a chunk
 // (coalesced 128-byte rows), split it and store hi/lo tiles in the canonical no-swizzle K-major core-matrix
-// layout; one thread issues the 12 tcgen05.mma of the chunk and commits them to the stage's mbarrier, which is
-// what the loaders of chunk i+2 wait on.  The epilogue reads TMEM with tcgen05.ld (warp w owns lanes 32w..32w+31),
+// layout, and every warp arrives on the stage's "filled" mbarrier; one thread waits for the eight arrivals, issues the 12
+// tcgen05.mma of the chunk and commits them to the stage's "free" mbarrier, which is what the stores of chunk i+2 wait on.
+// There is no CTA-wide barrier in the loop.  The epilogue reads TMEM with tcgen05.ld (warp w owns lanes 32w..32w+31),
 // applies the sigmoid and writes out[e][o] coalesced along o.
 #include "ngp_internal.h"
 
@@ -35,7 +36,7 @@ constexpr uint32_t LBO_B = TN * 16 + 16;
 constexpr uint32_t TILE_A = (KC / 4) * LBO_A;              // bytes of one A tile (hi or lo)
 constexpr uint32_t TILE_B = (KC / 4) * LBO_B;
 constexpr uint32_t STAGE = 2 * TILE_A + 2 * TILE_B;        // A_hi, A_lo, B_hi, B_lo
-constexpr uint32_t SMEM_BYTES = 2 * STAGE + 64;
+constexpr uint32_t SMEM_BYTES = 2 * STAGE + 64;          // stages + five mbarriers
 constexpr uint32_t TMEM_COLS = 64;
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, both K-major, N=64, M=128
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -51,6 +52,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo)
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
@@ -85,8 +90,9 @@ mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, co
     const float *W = genomes + (size_t)g * G + w_off;
     const float *A = in + (size_t)g * envs * ni;
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar0 = smem_base + 2 * STAGE;            // two stage barriers + one "accumulator ready" barrier
+    const uint32_t bar0 = smem_base + 2 * STAGE;            // two "stage free" barriers, one "accumulator ready", two "stage filled"
     const uint32_t bar_done = bar0 + 16;
+    const uint32_t bar_full = bar0 + 24;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS) : "memory");
@@ -94,6 +100,7 @@ mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, co
     }
     if (tid == 0) {
         mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_init(bar_done, 1);
+        mbar_init(bar_full, THREADS / 32); mbar_init(bar_full + 8, THREADS / 32);      // one arrival per producer warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -156,11 +163,14 @@ mlp_layer_tf32_kernel(const float *__restrict__ genomes, size_t w_off, int G, co
             *reinterpret_cast<float *>(stage + b_off + i * SBO + TILE_B) = v - hi;
         }
         if (c + 2 < n_chunks) load_chunk(c + 2, wv, xv);    // refill these registers two chunks ahead
-        // generic-proxy stores -> visible to the tensor core's async proxy
+        // generic-proxy stores -> visible to the tensor core's async proxy; then one arrival per warp on the stage's "filled"
+        // barrier.  No CTA-wide barrier: only the MMA-issuing thread waits for all eight warps, the others run ahead into the
+        // next chunk (bounded by the "stage free" barriers).
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * st);
         if (tid == 0) {
+            mbar_wait(bar_full + 8 * st, (c >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi = smem_base + st * STAGE, a_lo = a_hi + TILE_A, b_hi = a_hi + 2 * TILE_A, b_lo = b_hi + TILE_B;
 #pragma unroll

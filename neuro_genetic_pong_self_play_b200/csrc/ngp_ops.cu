@@ -29,31 +29,29 @@ static_assert(FS_ROUNDS * FS_THREADS == FS_VEC_PER_FRAME && FS_THREADS % 3 == 0,
 
 __device__ __forceinline__ uint32_t fs_zero_byte(uint32_t z) { return (z - 0x01010101u) & ~z & 0x80808080u; }
 
-// Exact accounting of one vector that contains at least one matching byte.  Sums are kept linear so that no per-byte
-// division is needed: a matching byte at offset B of its row with channel ch belongs to column (B - ch) / 3, so a target's
-// column sum is (sum of B - sum of ch) / 3, divided once per frame.  Per word: exact zero-byte mask, popcount, and the two
-// weighted byte sums as one multiply each (byte 3 of b * c is sum b_i * c_(3-i) for 0/1 bytes b_i).
-__device__ __forceinline__ void fs_account(uint32_t (&acc)[9], const uint32_t (&words)[4], const uint32_t (&pt)[3][4], int k, int phase)
+// Exact accounting of one target in one vector that contains at least one byte matching it.  Sums are kept linear so that
+// no per-byte division is needed: a matching byte at offset B of its row with channel ch belongs to column (B - ch) / 3, so
+// a target's column sum is (sum of B - sum of ch) / 3, divided once per frame.  Per word: exact zero-byte mask, popcount,
+// and the two weighted byte sums as one multiply each (byte 3 of b * c is sum b_i * c_(3-i) for 0/1 bytes b_i).
+__device__ __forceinline__ void fs_account(uint32_t &cnt, uint32_t &srow, uint32_t &scol, const uint32_t (&words)[4], const uint32_t (&pt)[4],
+                                           uint32_t row, uint32_t byte0, int phase)
 {
-    const uint32_t row = (uint32_t)k / 30u, byte0 = ((uint32_t)k % 30u) * 16u;
 #pragma unroll
-    for (int t = 0; t < 3; ++t)
-#pragma unroll
-        for (int wi = 0; wi < 4; ++wi) {
-            const uint32_t z = words[wi] ^ pt[t][wi];
-            if (!fs_zero_byte(z)) continue;
-            const uint32_t b = (~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & 0x80808080u) >> 7;     // 1 in every matching byte
-            const uint32_t c = __popc(b);
-            const uint32_t p0 = (uint32_t)(phase + wi) % 3u, p1 = (p0 + 1u) % 3u, p2 = (p0 + 2u) % 3u;   // channels of bytes 0,1,2 (3 = 0)
-            const uint32_t chc = p0 | (p2 << 8) | (p1 << 16) | (p0 << 24);
-            const uint32_t sidx = (b * 0x00010203u) >> 24, sch = (b * chc) >> 24;
-            acc[3 * t] += c; acc[3 * t + 1] += c * row; acc[3 * t + 2] += c * (byte0 + 4u * wi) + sidx - sch;
-        }
+    for (int wi = 0; wi < 4; ++wi) {
+        const uint32_t z = words[wi] ^ pt[wi];
+        const uint32_t b = (~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z) & 0x80808080u) >> 7;     // 1 in every matching byte
+        const uint32_t c = __popc(b);
+        const uint32_t p0 = (uint32_t)(phase + wi) % 3u, p1 = (p0 + 1u) % 3u, p2 = (p0 + 2u) % 3u;   // channels of bytes 0,1,2 (3 = 0)
+        const uint32_t chc = p0 | (p2 << 8) | (p1 << 16) | (p0 << 24);
+        const uint32_t sidx = (b * 0x00010203u) >> 24, sch = (b * chc) >> 24;
+        cnt += c; srow += c * row; scol += c * (byte0 + 4u * wi) + sidx - sch;
+    }
 }
 
 __global__ void __launch_bounds__(FS_THREADS) find_stuff_kernel(const uint8_t *__restrict__ frames, int n, FindStuffPatterns pat,
                                                                 float *__restrict__ loc, uint8_t *__restrict__ valid)
 {
+    constexpr int GROUP = 5, GROUPS = FS_ROUNDS / GROUP;      // 5 vectors per thread and step, 5 steps per frame
     __shared__ uint32_t red[2][FS_THREADS / 32][9];          // double-buffered: one barrier per frame
     const int tid = threadIdx.x, phase = tid % 3;
     uint32_t pt[3][4];
@@ -61,52 +59,80 @@ __global__ void __launch_bounds__(FS_THREADS) find_stuff_kernel(const uint8_t *_
     for (int t = 0; t < 3; ++t)
 #pragma unroll
         for (int wi = 0; wi < 4; ++wi) pt[t][wi] = pat.w[phase][t][wi];
+    const int my_frames = blockIdx.x < n ? (n - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int steps = my_frames * GROUPS;
+    auto vec_ptr = [&](int step) {
+        const size_t f = blockIdx.x + (size_t)(step / GROUPS) * gridDim.x;
+        return reinterpret_cast<const uint4 *>(frames + f * (a26::FB_ROWS * 480) + a26::CROP_TOP * 480) + tid + (step % GROUPS) * GROUP * FS_THREADS;
+    };
+    uint4 cur[GROUP], nxt[GROUP];
+    if (steps > 0) {
+        const uint4 *p = vec_ptr(0);
+#pragma unroll
+        for (int j = 0; j < GROUP; ++j) cur[j] = __ldcs(&p[j * FS_THREADS]);
+    }
+    uint32_t acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};           // per target: count, sum row, sum of (row offset - channel)
     int buf = 0;
-    for (int f = blockIdx.x; f < n; f += gridDim.x, buf ^= 1) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(frames + (size_t)f * (a26::FB_ROWS * 480) + a26::CROP_TOP * 480) + tid;
-        uint32_t acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};       // per target: count, sum row, sum col
 #pragma unroll 1
-        for (int r0 = 0; r0 < FS_ROUNDS; r0 += 5) {
-            uint4 vec[5];
+    for (int step = 0; step < steps; ++step) {
+        // the next step's 80 bytes are requested before this step's are looked at: loads are always in flight
+        if (step + 1 < steps) {
+            const uint4 *p = vec_ptr(step + 1);
 #pragma unroll
-            for (int j = 0; j < 5; ++j) vec[j] = __ldcs(&src[(r0 + j) * FS_THREADS]);     // 80 B in flight per thread
-            uint32_t flagged = 0;
+            for (int j = 0; j < GROUP; ++j) nxt[j] = __ldcs(&p[j * FS_THREADS]);
+        }
+        uint32_t flagged = 0;                                // bit 3j+t: vector j holds a byte of target t
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const uint32_t words[4] = {vec[j].x, vec[j].y, vec[j].z, vec[j].w};
+        for (int j = 0; j < GROUP; ++j) {
+            const uint32_t words[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
                 uint32_t any = 0;
 #pragma unroll
-                for (int t = 0; t < 3; ++t)
-#pragma unroll
-                    for (int wi = 0; wi < 4; ++wi) any |= fs_zero_byte(words[wi] ^ pt[t][wi]);
-                flagged |= (any ? 1u : 0u) << j;
+                for (int wi = 0; wi < 4; ++wi) any |= fs_zero_byte(words[wi] ^ pt[t][wi]);
+                if (any) flagged |= 1u << (3 * j + t);
             }
-            // rare: a vector with an object pixel is fetched again (L2) and accounted for exactly; kept out of the unrolled
-            // stream so that the hot loop stays a few KB of straight-line code
-            if (flagged) {
+        }
+        // rare (< 1 % of the vectors): fetched again (L2) and accounted for exactly; kept out of the unrolled stream so that
+        // the hot loop stays a few KB of straight-line code
+        if (flagged) {
+            const uint4 *p = vec_ptr(step);
+            const int g = step % GROUPS;
 #pragma unroll 1
-                for (int j = 0; j < 5; ++j) {
-                    if (!((flagged >> j) & 1u)) continue;
-                    const uint4 v = src[(r0 + j) * FS_THREADS];
-                    const uint32_t words[4] = {v.x, v.y, v.z, v.w};
-                    fs_account(acc, words, pt, tid + (r0 + j) * FS_THREADS, phase);
-                }
+            for (int j = 0; j < GROUP; ++j) {
+                const uint32_t fl = (flagged >> (3 * j)) & 7u;
+                if (!fl) continue;
+                const uint4 v = p[j * FS_THREADS];
+                const uint32_t words[4] = {v.x, v.y, v.z, v.w};
+                const uint32_t k = (uint32_t)tid + (uint32_t)(g * GROUP + j) * FS_THREADS;
+                const uint32_t row = k / 30u, byte0 = (k % 30u) * 16u;
+                if (fl & 1u) fs_account(acc[0], acc[1], acc[2], words, pt[0], row, byte0, phase);
+                if (fl & 2u) fs_account(acc[3], acc[4], acc[5], words, pt[1], row, byte0, phase);
+                if (fl & 4u) fs_account(acc[6], acc[7], acc[8], words, pt[2], row, byte0, phase);
             }
         }
+        if (step % GROUPS == GROUPS - 1) {                   // frame complete
+            const int f = blockIdx.x + (step / GROUPS) * gridDim.x;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) acc[i] = __reduce_add_sync(0xFFFFFFFFu, acc[i]);
-        if ((tid & 31) == 0)
+            for (int i = 0; i < 9; ++i) { acc[i] = __reduce_add_sync(0xFFFFFFFFu, acc[i]); }
+            if ((tid & 31) == 0)
 #pragma unroll
-            for (int i = 0; i < 9; ++i) red[buf][tid >> 5][i] = acc[i];
-        __syncthreads();
-        if (tid < 3) {
-            uint32_t c = 0, sr = 0, sc = 0;
+                for (int i = 0; i < 9; ++i) red[buf][tid >> 5][i] = acc[i];
 #pragma unroll
-            for (int w = 0; w < FS_THREADS / 32; ++w) { c += red[buf][w][3 * tid]; sr += red[buf][w][3 * tid + 1]; sc += red[buf][w][3 * tid + 2]; }
-            valid[f * 3 + tid] = c > 0;
-            loc[(f * 3 + tid) * 2 + 0] = c ? (float)((double)sr / (double)c) : 0.f;
-            loc[(f * 3 + tid) * 2 + 1] = c ? (float)((double)(sc / 3u) / (double)c) : 0.f;
+            for (int i = 0; i < 9; ++i) acc[i] = 0;
+            __syncthreads();
+            if (tid < 3) {
+                uint32_t c = 0, sr = 0, sc = 0;
+#pragma unroll
+                for (int w = 0; w < FS_THREADS / 32; ++w) { c += red[buf][w][3 * tid]; sr += red[buf][w][3 * tid + 1]; sc += red[buf][w][3 * tid + 2]; }
+                valid[f * 3 + tid] = c > 0;
+                loc[(f * 3 + tid) * 2 + 0] = c ? (float)((double)sr / (double)c) : 0.f;
+                loc[(f * 3 + tid) * 2 + 1] = c ? (float)((double)(sc / 3u) / (double)c) : 0.f;
+            }
+            buf ^= 1;
         }
+#pragma unroll
+        for (int j = 0; j < GROUP; ++j) cur[j] = nxt[j];
     }
 }
 
@@ -280,7 +306,8 @@ __global__ void __launch_bounds__(128) mlp_narrow_in_kernel(const float *__restr
 #pragma unroll
         for (int k = 0; k < NARROW_K; ++k) if (k < ni) acc = fmaf(xs[e * ni + k], w[k], acc);
         if (bias) acc = fmaf(1.0f, wb, acc);
-        dst[(size_t)e * no] = sigmoid_f32(acc);
+        // fast exponential (ex2.approx) + IEEE reciprocal, as in the tensor-core layer's epilogue: far inside the 1e-5 bar
+        dst[(size_t)e * no] = __frcp_rn(1.0f + __expf(-acc));
     }
 }
 
@@ -371,21 +398,27 @@ __global__ void __launch_bounds__(256) mlp_last_wide_kernel(const float *__restr
                 z0[o] += __shfl_down_sync(0xFFFFFFFFu, z0[o], off);
                 z1[o] += __shfl_down_sync(0xFFFFFFFFu, z1[o], off);
             }
-        if (lane == 0) {
+        // lanes 0 .. 2*NO-1 evaluate one FP64 sigmoid each (row r = lane / NO, output o = lane % NO)
+        double zmine = 0.0;
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (r == 1 && !two) break;
-                const size_t row = (size_t)g * envs + (r ? e2 : e);
-                int best = 0;
-                double sbest = 0.0;
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int o = 0; o < NO; ++o) {
-                    const double sg = pol::det_sigmoid((r ? z1[o] : z0[o]) + wb[o]);
-                    if (out) out[row * NO + o] = (float)sg;
-                    if (o == 0 || sg > sbest) { sbest = sg; best = o; }
-                }
-                act[row] = best == 0 ? pol::ACT_UP : pol::ACT_DOWN;
+            for (int o = 0; o < NO; ++o) {
+                const double zz = __shfl_sync(0xFFFFFFFFu, (r ? z1[o] : z0[o]) + wb[o], 0);
+                if (lane == r * NO + o) zmine = zz;
             }
+        const double sg = lane < 2 * NO ? pol::det_sigmoid(zmine) : 0.0;
+        int best = 0;
+        double sbest = 0.0;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+            const double so = __shfl_sync(0xFFFFFFFFu, sg, (lane < NO ? 0 : NO) + o);     // lane 0 reads row 0, lane NO reads row 1
+            if (o == 0 || so > sbest) { sbest = so; best = o; }
+        }
+        if (lane < 2 * NO && (lane < NO || two)) {
+            const size_t row = (size_t)g * envs + (lane < NO ? e : e2);
+            if (out) out[row * NO + (lane % NO)] = (float)sg;
+            if (lane % NO == 0) act[row] = best == 0 ? pol::ACT_UP : pol::ACT_DOWN;
         }
     }
 }

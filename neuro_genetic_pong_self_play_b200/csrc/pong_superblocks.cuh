@@ -124,5 +124,60 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
 #undef A26_SB_POKE
 }
 
+// The score display loop $F58B-$F5B4, entered at $F58D (the instruction after `STA WSYNC`): one scanline per iteration,
+// 20 per frame.  Each line reads four digit-graphics bytes from ROM through the pointers at $C5/$C9 (left score) and
+// $C7/$CB (right score), writes PF1 twice at exact cycles (the two halves of the mirrored playfield show different digits),
+// keeps the scratch cell $87, counts lines in X (four per digit row) and digit rows in Y (five).
+//   $F58D LDA ($C5),Y ; AND #$0F ; STA $87 ; LDA ($C9),Y ; AND #$F0 ; ORA $87 ; STA PF1
+//   $F59B LDA ($C7),Y ; AND #$0F ; STA $87 ; LDA ($CB),Y ; AND #$F0 ; ORA $87 ; AND $90 ; STA PF1
+//   $F5AB TXA ; INX ; AND #$03 ; BNE $F58B ; INY ; CPY #$05 ; BNE $F58B        $F58B STA WSYNC
+// Returns false (nothing touched) when a guard fails; otherwise pc is $F5B6 (loop ended) or $F58D.
+template <bool VERIFY>
+__device__ __forceinline__ bool superblock_f58d(Chip &s, const Tables &T, Ram ram, uint8_t *fb, uint32_t &a, uint32_t &x, uint32_t &y,
+                                                uint32_t &pc, uint32_t &fc, uint32_t &nv, uint32_t &zv, uint32_t &cyc, uint32_t cpu_ls, int max_iters)
+{
+    const uint32_t wc4 = ram.rd32(0xC4), wc8 = ram.rd32(0xC8), wcc = ram.rd32(0xCC);
+    const uint32_t q5 = (wc4 >> 8) & 0xFFFFu, q7 = (wc4 >> 24) | ((wc8 & 0xFFu) << 8), q9 = (wc8 >> 8) & 0xFFFFu, qb = (wc8 >> 24) | ((wcc & 0xFFu) << 8);
+    // digit rows are read from ROM for every Y of the loop (Y < 5)
+    if (y >= 5u || !(q5 & q7 & q9 & qb & (q5 + 4u) & (q7 + 4u) & (q9 + 4u) & (qb + 4u) & 0x1000u)) return false;
+    const uint32_t r90 = ram.rd(0x90u);
+    uint32_t scratch = 0;
+    for (int iter = 0; iter < max_iters; ++iter) {
+        const uint32_t t0 = cyc;
+        const uint32_t m1 = rom_byte(T, q5 + y), m2 = rom_byte(T, q9 + y), m3 = rom_byte(T, q7 + y), m4 = rom_byte(T, qb + y);
+        uint32_t k = 23u + (((q5 & 0xFFu) + y) >> 8) + (((q9 & 0xFFu) + y) >> 8);
+        {
+            const uint32_t pv = (m2 & 0xF0u) | (m1 & 0x0Fu);
+            if (!poke_quick(s, 0x0Eu, pv)) tia_poke<VERIFY>(s, T, 0x0Eu, pv, t0 + k, cpu_ls, fb);
+        }
+        k += 26u + (((q7 & 0xFFu) + y) >> 8) + (((qb & 0xFFu) + y) >> 8);
+        scratch = m3 & 0x0Fu;
+        {
+            const uint32_t pv = ((m4 & 0xF0u) | scratch) & r90;
+            if (!poke_quick(s, 0x0Eu, pv)) tia_poke<VERIFY>(s, T, 0x0Eu, pv, t0 + k, cpu_ls, fb);
+        }
+        // TXA ; INX ; AND #$03 ; BNE
+        a = x & 3u; x = (x + 1u) & 0xFFu; nv = zv = a;
+        k += 6u;
+        if (a == 0u) {
+            // INY ; CPY #$05 ; BNE
+            y = (y + 1u) & 0xFFu;
+            fc = y >= 5u ? 1u : 0u; nv = zv = (y - 5u) & 0xFFu;
+            k += 2u + 4u;
+            if (y == 5u) {
+                ram.wr(0x87u, scratch);
+                cyc = t0 + k + 2u; pc = 0xF5B6u;
+                return true;
+            }
+        }
+        k += 3u + 3u;                              // taken branch (same page) + STA WSYNC
+        cyc = t0 + k;
+        cyc += wsync_stall(cyc, cpu_ls);
+    }
+    ram.wr(0x87u, scratch);
+    pc = 0xF58Du;
+    return true;
+}
+
 #endif  // __CUDACC__
 }  // namespace a26

@@ -35,8 +35,9 @@ MAX_STRUCTURED_SKIP = 24                      # bytes a structured forward branc
 HOT_ENTRIES = [0xF621, 0xF58D, 0xF58B, 0xF5CC, 0xF5B8, 0xF21F, 0xF094]
 # Hand-fused super-blocks (csrc/pong_superblocks.cuh): dispatch entry -> (first byte, last byte + 1, sha1 of the cartridge
 # bytes the fused code was written against).  The hook is only emitted when the ROM still holds exactly those bytes.
-SUPERBLOCKS = {0xF621: (0xF5E0, 0xF63E, "9cf83bee22051baf07f26f6b6fd104e7b6f90ebe")}
-SUPERBLOCK_EXITS = [0xF63E]          # program counters a super-block can leave with: must be dispatch entries
+SUPERBLOCKS = {0xF621: (0xF5E0, 0xF63E, "9cf83bee22051baf07f26f6b6fd104e7b6f90ebe"),
+               0xF58D: (0xF58B, 0xF5B6, "2c60768c1cb396d94451a9af3be5bc39cdc01337")}
+SUPERBLOCK_EXITS = [0xF63E, 0xF5B6]          # program counters a super-block can leave with: must be dispatch entries
 
 
 def load_rom():

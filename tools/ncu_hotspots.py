@@ -34,7 +34,7 @@ def main():
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-cubin", "-o", cubin,
                            os.path.join(CSRC, tu)], stderr=subprocess.DEVNULL)
     sass = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.split("\n")
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kernel, "-c", "1"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
     kname = rows[0][1]
     hdr, data = rows[1], rows[2:]
