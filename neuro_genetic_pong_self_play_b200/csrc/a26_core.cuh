@@ -131,7 +131,7 @@ struct Chip {
     uint8_t grp1_new, grp1_old, enam0, enam1, enabl_new, enabl_old, hmp0, hmp1;
     uint8_t hmm0, hmm1, hmbl, vdelp0, vdelp1, vdelbl, resmp0, resmp1;
     uint8_t posp0, posp1, posm0, posm1, posbl, suppress, hmove_blank, frame_done;
-    uint8_t swcha, swchb, dump_enabled, keyrep, error, pad0, pad1, pad2;
+    uint8_t swcha, swchb, dump_enabled, keyrep, error, pf_dirty, pad1, pad2;   // pf_dirty: pfmask[] is stale (rebuilt on use)
     uint16_t cx, pad3;
     // renderer
     int32_t line;            // TIA scanline relative to the frame start
@@ -178,8 +178,7 @@ struct Masks { uint32_t w[5]; };
 
 __device__ __forceinline__ uint32_t rom_byte(const Tables &T, uint32_t addr)
 {
-    uint32_t a = addr & 0x7FF;
-    return (T.rom[a >> 2] >> ((a & 3) * 8)) & 0xFF;
+    return reinterpret_cast<const uint8_t *>(T.rom)[addr & 0x7FF];      // little-endian words: one byte load
 }
 
 // ---- RAM: word-interleaved shared memory ---------------------------------------------------
@@ -341,16 +340,29 @@ __device__ __forceinline__ bool quick_missile(QuickObj &o, uint32_t nusiz, uint3
     o.start = (int)pos; o.width = width; o.pat = (1u << width) - 1u; o.colour = colour;
     return true;
 }
-static __device__ __noinline__ bool render_span_quick(Chip &s, const Tables &T, int x0, int x1, int row_lo, int row_hi)
+// One to three rectangles [x0,x1) x [row_lo,row_hi) that share the current register state (a catch-up over several
+// scanlines is "rest of the current line, whole lines, start of the target line"): the latches are read and the objects
+// classified once.
+struct QuickPart { int x0, x1, row_lo, row_hi; };
+template <int NPARTS>
+__device__ __forceinline__ bool render_parts_quick(Chip &s, const Tables &T, const QuickPart (&part)[NPARTS])
 {
     const uint32_t grp0 = (s.vdelp0 & 1) ? s.grp0_old : s.grp0_new, grp1 = (s.vdelp1 & 1) ? s.grp1_old : s.grp1_new;
     const bool bl_on = (((s.vdelbl & 1) ? s.enabl_old : s.enabl_new) & 2) != 0;
     const bool m0_on = (s.enam0 & 2) && !(s.resmp0 & 2), m1_on = (s.enam1 & 2) && !(s.resmp1 & 2);
-    // rows [row_lo, row_hi) of the display window share this state; only those inside the crop count
-    const int clo = row_lo < CROP_TOP ? CROP_TOP : row_lo, chi = row_hi > CROP_BOTTOM ? CROP_BOTTOM : row_hi;
-    const bool in_crop = chi > clo;
-    const bool pf_any = (s.pfmask[0] | s.pfmask[1] | s.pfmask[2] | s.pfmask[3] | s.pfmask[4]) != 0;
-    const bool comb = s.hmove_blank && x0 < 8;
+    // only rows inside the crop count; a part with no pixels inside it needs nothing
+    uint32_t nrows[NPARTS], rowsum[NPARTS];
+    bool in_crop = false, comb = false;
+#pragma unroll
+    for (int p = 0; p < NPARTS; ++p) {
+        const int clo = part[p].row_lo < CROP_TOP ? CROP_TOP : part[p].row_lo, chi = part[p].row_hi > CROP_BOTTOM ? CROP_BOTTOM : part[p].row_hi;
+        const bool live = chi > clo && part[p].x1 > part[p].x0;
+        nrows[p] = live ? (uint32_t)(chi - clo) : 0u;
+        rowsum[p] = nrows[p] * (uint32_t)(clo - CROP_TOP) + nrows[p] * (nrows[p] - 1) / 2;   // sum of cropped row indices
+        in_crop = in_crop || live;
+        comb = comb || (s.hmove_blank && part[p].x0 < 8 && part[p].x1 > part[p].x0);
+    }
+    const bool pf_any = ((s.pf0 & 0xF0) | s.pf1 | s.pf2) != 0;
     if (!(grp0 | grp1) && !bl_on && !m0_on && !m1_on) {
         if (!in_crop) return true;
         uint32_t wts = T.weight[s.colubk >> 1];
@@ -381,30 +393,50 @@ static __device__ __noinline__ bool render_span_quick(Chip &s, const Tables &T, 
         for (int j = i + 1; j < 5; ++j)
             if (on[i] && on[j] && o[i].start < o[j].start + o[j].width && o[j].start < o[i].start + o[i].width) return false;
     if (!in_crop) return true;
-    const uint32_t nrows = (uint32_t)(chi - clo);
-    const uint32_t rowsum = nrows * (uint32_t)(clo - CROP_TOP) + nrows * (nrows - 1) / 2;   // sum of cropped row indices
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         if (!on[i]) continue;
         const uint32_t wts = T.weight[o[i].colour >> 1];
         if (!wts) continue;
-        int lo = x0 - o[i].start, hi = x1 - o[i].start;
-        lo = lo < 0 ? 0 : lo; hi = hi > o[i].width ? o[i].width : hi;
-        if (hi <= lo) continue;
-        const uint32_t clip = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-        const uint32_t q = o[i].pat & clip;
-        if (!q) continue;
-        const uint32_t n = __popc(q), sx = n * (uint32_t)o[i].start + bit_index_sum(q);
+        uint32_t n_r = 0, sx_r = 0, n_y = 0;             // pixels x rows, column sums x rows, pixels x row-index sums
+#pragma unroll
+        for (int p = 0; p < NPARTS; ++p) {
+            if (!nrows[p]) continue;
+            int lo = part[p].x0 - o[i].start, hi = part[p].x1 - o[i].start;
+            lo = lo < 0 ? 0 : lo; hi = hi > o[i].width ? o[i].width : hi;
+            if (hi <= lo) continue;
+            const uint32_t clip = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+            const uint32_t q = o[i].pat & clip;
+            if (!q) continue;
+            const uint32_t n = __popc(q), sx = n * (uint32_t)o[i].start + bit_index_sum(q);
+            n_r += n * nrows[p]; sx_r += sx * nrows[p]; n_y += n * rowsum[p];
+        }
+        if (!n_r) continue;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
             const uint32_t w = (wts >> (2 * t)) & 3;
-            s.cnt[t] += w * n * nrows; s.sx[t] += w * sx * nrows; s.sy[t] += w * n * rowsum;
+            s.cnt[t] += w * n_r; s.sx[t] += w * sx_r; s.sy[t] += w * n_y;
         }
     }
     return true;
 }
+static __device__ __noinline__ bool render_span_quick(Chip &s, const Tables &T, int x0, int x1, int row_lo, int row_hi)
+{
+    const QuickPart part[1] = {{x0, x1, row_lo, row_hi}};
+    return render_parts_quick<1>(s, T, part);
+}
+// Catch-up over a line boundary in the fused mode: the rest of the current line [rx,160), `full` whole lines and the first
+// xc pixels of the target line, all with the current register state.  Only valid while no per-line state is pending
+// (HMOVE blanking, RESPx suppression: both are cleared at the next line start, so the first line would differ).
+// Returns false with nothing changed when the quick rules do not apply.
+static __device__ __noinline__ bool catchup_quick(Chip &s, const Tables &T, int full, int xc)
+{
+    const int row0 = s.line - YSTART;
+    // rows outside the display window have no pixels: clip the row ranges to it (the crop lies inside the window)
+    const QuickPart part[3] = {{s.rx, FB_COLS, row0, row0 + 1}, {0, FB_COLS, row0 + 1, row0 + 1 + full}, {0, xc, row0 + 1 + full, row0 + 2 + full}};
+    return render_parts_quick<3>(s, T, part);
+}
 
-// Render pixels [x0, x1) of the TIA's current scanline (display row `row`), VBLANK off.
 template <bool VERIFY>
 __device__ __noinline__ void render_span(Chip &s, const Tables &T, int x0, int x1, int row, uint8_t *fb_row)
 {
@@ -415,6 +447,8 @@ __device__ __noinline__ void render_span(Chip &s, const Tables &T, int x0, int x
     const bool in_crop_row = row >= CROP_TOP && row < CROP_BOTTOM;
     A26_STAT(3);
     Masks R, PF, BL, P0, P1, M0, M1;
+#pragma unroll
+    if (s.pf_dirty) { rebuild_pfmask(s); s.pf_dirty = 0; }
 #pragma unroll
     for (int i = 0; i < 5; ++i) { R.w[i] = range_word(i, x0, x1); PF.w[i] = s.pfmask[i] & R.w[i]; }
     // ball
@@ -553,6 +587,16 @@ __device__ __forceinline__ void render_full_lines(Chip &s, const Tables &T, int 
 template <bool VERIFY>
 __device__ __forceinline__ void tia_catchup(Chip &s, const Tables &T, int h, uint8_t *fb)
 {
+    if (!VERIFY && h > LINE_CLOCKS && !(s.hmove_blank | s.suppress) && !(s.vblank & 2)) {
+        // several lines with one register state: one classification of the objects for all of them
+        const int hh = h - LINE_CLOCKS, full = (hh - 1) / LINE_CLOCKS;
+        int xc = hh - full * LINE_CLOCKS - HBLANK_CLOCKS;
+        xc = xc < 0 ? 0 : (xc > FB_COLS ? FB_COLS : xc);
+        if (catchup_quick(s, T, full, xc)) {
+            s.line += 1 + full; s.tia_ls += (uint32_t)(1 + full) * LINE_CYCLES; s.rx = xc;
+            return;
+        }
+    }
     if (h > LINE_CLOCKS) {
         render_to<VERIFY>(s, T, FB_COLS, fb);                           // finish the current line
         tia_newline(s, 1);
@@ -626,6 +670,30 @@ __device__ __forceinline__ void tia_apply(Chip &s, const Tables &T, uint32_t reg
 {
     A26_STAT(1);
     A26_STAT_REG(reg);
+    if (!VERIFY && reg >= 0x06 && reg <= 0x0F && reg != 0x0B && reg != 0x0C) {
+        // Fused mode, playfield / colour registers while no movable object is enabled: nothing can collide, and rows outside
+        // the crop add nothing to the observation whatever the registers hold.  When everything between the renderer's
+        // position and this write lies above the crop (score area) or below it, the renderer is left where it is (it will
+        // cross those rows later with the new values, to the same effect: none) and only the latch changes.
+        const int crop_first = YSTART + CROP_TOP, crop_end = YSTART + CROP_BOTTOM;     // TIA lines of the crop
+        const bool above = s.line < crop_first &&
+                           (int32_t)(cyc_after + 4u - (s.tia_ls + (uint32_t)(crop_first - s.line) * LINE_CYCLES)) < 0;   // +4: write delay
+        const bool below = s.line >= crop_end && !s.frame_done;
+        const bool objects = (s.grp0_new | s.grp0_old | s.grp1_new | s.grp1_old) != 0 || ((s.enam0 | s.enam1 | s.enabl_new | s.enabl_old) & 2) != 0;
+        if ((above || below) && !objects) {
+            switch (reg) {
+            case 0x06: s.colup0 = (uint8_t)v; break;
+            case 0x07: s.colup1 = (uint8_t)v; break;
+            case 0x08: s.colupf = (uint8_t)v; break;
+            case 0x09: s.colubk = (uint8_t)v; break;
+            case 0x0A: s.ctrlpf = (uint8_t)v; s.pf_dirty = 1; break;
+            case 0x0D: s.pf0 = (uint8_t)v; s.pf_dirty = 1; break;
+            case 0x0E: s.pf1 = (uint8_t)v; s.pf_dirty = 1; break;
+            default: s.pf2 = (uint8_t)v; s.pf_dirty = 1; break;
+            }
+            return;
+        }
+    }
     const int hpos = 3 * (int)cil;
     int delay = 0;
     switch (reg) {
@@ -656,12 +724,12 @@ __device__ __forceinline__ void tia_apply(Chip &s, const Tables &T, uint32_t reg
     case 0x07: s.colup1 = (uint8_t)v; break;
     case 0x08: s.colupf = (uint8_t)v; break;
     case 0x09: s.colubk = (uint8_t)v; break;
-    case 0x0A: s.ctrlpf = (uint8_t)v; rebuild_pfmask(s); break;
+    case 0x0A: s.ctrlpf = (uint8_t)v; s.pf_dirty = 1; break;
     case 0x0B: s.refp0 = (uint8_t)v; break;
     case 0x0C: s.refp1 = (uint8_t)v; break;
-    case 0x0D: s.pf0 = (uint8_t)v; rebuild_pfmask(s); break;
-    case 0x0E: s.pf1 = (uint8_t)v; rebuild_pfmask(s); break;
-    case 0x0F: s.pf2 = (uint8_t)v; rebuild_pfmask(s); break;
+    case 0x0D: s.pf0 = (uint8_t)v; s.pf_dirty = 1; break;
+    case 0x0E: s.pf1 = (uint8_t)v; s.pf_dirty = 1; break;
+    case 0x0F: s.pf2 = (uint8_t)v; s.pf_dirty = 1; break;
     case 0x10: s.posp0 = (uint8_t)(hpos < HBLANK_CLOCKS ? 3 : (hpos - HBLANK_CLOCKS + 5) % 160); s.suppress |= 1; break;
     case 0x11: s.posp1 = (uint8_t)(hpos < HBLANK_CLOCKS ? 3 : (hpos - HBLANK_CLOCKS + 5) % 160); s.suppress |= 2; break;
     case 0x12: s.posm0 = (uint8_t)(hpos < HBLANK_CLOCKS ? 2 : (hpos - HBLANK_CLOCKS + 4) % 160); break;
@@ -704,13 +772,19 @@ __device__ __forceinline__ void tia_apply(Chip &s, const Tables &T, uint32_t reg
 
 // TIA register write.  cyc_after = CPU cycle count after the write cycle; cpu_ls = a CPU cycle at
 // which some scanline started.  Returns the number of cycles the CPU stalls (WSYNC).
+// tia_poke_changed: for callers that have already seen poke_quick() fail for this write (and reg != WSYNC).
 template <bool VERIFY>
-__device__ __noinline__ uint32_t tia_poke(Chip &s, const Tables &T, uint32_t reg, uint32_t v, uint32_t cyc_after, uint32_t cpu_ls, uint8_t *fb)
+__device__ __noinline__ void tia_poke_changed(Chip &s, const Tables &T, uint32_t reg, uint32_t v, uint32_t cyc_after, uint32_t cpu_ls, uint8_t *fb)
 {
     A26_STAT(0);
+    tia_apply<VERIFY>(s, T, reg, v, cyc_after, (cyc_after - cpu_ls) % LINE_CYCLES, fb);
+}
+template <bool VERIFY>
+__device__ __forceinline__ uint32_t tia_poke(Chip &s, const Tables &T, uint32_t reg, uint32_t v, uint32_t cyc_after, uint32_t cpu_ls, uint8_t *fb)
+{
     if (reg == 0x02) return wsync_stall(cyc_after, cpu_ls);
     if (poke_quick(s, reg, v)) return 0;
-    tia_apply<VERIFY>(s, T, reg, v, cyc_after, (cyc_after - cpu_ls) % LINE_CYCLES, fb);
+    tia_poke_changed<VERIFY>(s, T, reg, v, cyc_after, cpu_ls, fb);
     return 0;
 }
 
@@ -807,8 +881,8 @@ __device__ __noinline__ uint32_t io_write_slow(Chip &s, const Tables &T, uint32_
         const uint32_t reg = addr & 0x3F;
         if (reg == 0x02) return wsync_stall(cyc_after, cpu_ls);
         if (poke_quick(s, reg, v)) return 0;
-        const uint32_t stall = tia_poke<VERIFY>(s, T, reg, v, cyc_after, cpu_ls, fb);
-        return stall | ((uint32_t)s.frame_done << 16);
+        tia_poke_changed<VERIFY>(s, T, reg, v, cyc_after, cpu_ls, fb);
+        return (uint32_t)s.frame_done << 16;
     }
     if ((addr & 0x1280) == 0x0280) riot_poke(s, addr, v, cyc_after);
     return 0;

@@ -7,7 +7,7 @@
 // `superblock_f621` computes exactly that in one straight-line block: same values, same write order, same
 // CPU cycle stamp on every write and read, no flag bookkeeping for results nobody reads.  The TIA sees the
 // same (register, value, cycle) sequence as from the instruction-by-instruction translation, through the same
-// poke_quick / tia_poke functions.
+// poke_quick / tia_poke_changed functions.
 //
 // tools/gen_rom_core.py only emits the hook when the cartridge bytes of the loop are the ones this code
 // was written against; the guards at the top fall back to the generic translation for any state the
@@ -47,7 +47,7 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
 #define A26_SB_POKE(REG_, V_, T_)                                                                              \
     do {                                                                                                       \
         const uint32_t pv_ = (V_);                                                                             \
-        if (!poke_quick(s, (REG_), pv_)) tia_poke<VERIFY>(s, T, (REG_), pv_, (T_), cpu_ls, fb);                \
+        if (!poke_quick(s, (REG_), pv_)) tia_poke_changed<VERIFY>(s, T, (REG_), pv_, (T_), cpu_ls, fb);                \
     } while (0)
     if (sp != 0x1Eu || (fid & 8u)) return false;
     // RAM cells the loop only reads (it writes $84/$85 and, through the stack pointer, TIA latches): loaded once
@@ -62,6 +62,11 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
     // paddle capacitors: dump state and thresholds only change in VBLANK code
     const bool dumped = s.dump_enabled != 0;
     const uint32_t dump_cyc = s.dump_cyc, need0 = s.needed[sel], need1 = s.needed[2u + sel];
+    // Steady state: when an iteration writes the same eight bytes as the two before it (inside this call), the latches
+    // -- including the old/new copies that GRP0/GRP1 writes shuffle -- are at the fixed point of that write sequence: every
+    // one of the eight writes would find its latch unchanged, so they are skipped without reading the latches.
+    uint32_t prev_a = 0, prev_b = 0;
+    int steady = 0;
     // bounded by the caller (at most one trip of X through its 8-bit range), then back through the dispatcher
     for (int iter = 0; iter < max_iters; ++iter) {
         const uint32_t x1 = (x + 1u) & 0xFFu, x2 = (x + 2u) & 0xFFu;
@@ -70,10 +75,10 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
         uint32_t r, c, v;
 
         // ---- $F621 STY GRP0 ; TXA ; SEC ; SBC $B5 ; AND $A8 ; PHP (sp=$1E -> ENAM1) ----
-        A26_SB_POKE(0x1Bu, y, t0 + 3u);
+        const uint32_t v_grp0 = y;                                      // written at t0 + 3
         sb_sbc(x, b5, r, c, v);
         r &= a8;
-        A26_SB_POKE(0x1Eu, sb_php(r, c, v, fid), t0 + 16u);
+        const uint32_t v_enam1 = sb_php(r, c, v, fid);                  // written at t0 + 16
         // ---- LDY $80 ; LDA $0038,Y ; BMI ; STX $84 ; LDA $003A,Y ; BMI ; STX $85 ----
         uint32_t k = 23u;
         const uint32_t in0 = (!dumped && (t0 + k - dump_cyc) > need0) ? 0x80u : 0u;
@@ -83,6 +88,8 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
         if (in1) k += 3u; else { ram.wr(0x85u, x); k += 5u; }
         // ---- CPX #$DC ; BNE $F5E0 ----
         if (x == 0xDCu) {
+            A26_SB_POKE(0x1Bu, v_grp0, t0 + 3u);
+            A26_SB_POKE(0x1Eu, v_enam1, t0 + 16u);
             a = in1; y = sel; sp = 0x1Du; fc = 1u; fv = v; nv = zv = 0u;
             cyc = t0 + k + 4u; pc = 0xF63Eu;
             return true;
@@ -94,27 +101,44 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
         // ---- TXA ; INX ; SEC ; SBC $B4 ; AND $A7 ; PHP (sp=$1D -> ENAM0) ; STY GRP1 ----
         sb_sbc(x, b4, r, c, v);
         r &= a7;
+        const uint32_t v_enam0 = sb_php(r, c, v, fid);
         k += 15u;
-        A26_SB_POKE(0x1Du, sb_php(r, c, v, fid), t0 + k);
+        const uint32_t t_enam0 = k;
         k += 3u;
-        A26_SB_POKE(0x1Cu, g1, t0 + k);
+        const uint32_t t_grp1 = k;
         // ---- TXA ; LSR ; LSR ; LSR ; TAY ; LDA ($9B),Y ; STA PF0 ; LDA ($9D),Y ; STA PF1 ; LDA ($9F),Y ; STA PF2 ----
         k += 10u;
         k += 8u + (((p0 & 0xFFu) + row) >> 8);
-        A26_SB_POKE(0x0Du, rom_byte(T, p0 + row), t0 + k);
+        const uint32_t t_pf0 = k, v_pf0 = rom_byte(T, p0 + row);
         k += 8u + (((p1 & 0xFFu) + row) >> 8);
-        A26_SB_POKE(0x0Eu, rom_byte(T, p1 + row), t0 + k);
+        const uint32_t t_pf1 = k, v_pf1 = rom_byte(T, p1 + row);
         k += 8u + (((p2 & 0xFFu) + row) >> 8);
-        A26_SB_POKE(0x0Fu, rom_byte(T, p2 + row), t0 + k);
+        const uint32_t t_pf2 = k, v_pf2 = rom_byte(T, p2 + row);
         // ---- INX ; TXA ; LDX #$1F ; TXS ; TAX ; LDY #$F0 ; SEC ; SBC $B2 ; AND $A5 ; BEQ ; LDY #$00 ----
         const uint32_t g0 = (((x2 - b2) & a5) & 0xFFu) == 0u ? 0xF0u : 0x00u;
         k += 20u + (g0 ? 3u : 4u);
         // ---- TXA ; SEC ; SBC $B6 ; AND #$FC ; PHP (sp=$1F -> ENABL) ; STX WSYNC ----
         sb_sbc(x2, b6, r, c, v);
         r &= 0xFCu;
+        const uint32_t v_enabl = sb_php(r, c, v, fid);
         k += 12u;
-        A26_SB_POKE(0x1Fu, sb_php(r, c, v, fid), t0 + k);
+        const uint32_t t_enabl = k;
         k += 3u;
+        // ---- the eight latch writes, in program order with their cycle stamps (nothing in between reads TIA state) ----
+        const uint32_t pack_a = v_grp0 | (v_enam1 << 8) | (v_enam0 << 16) | (g1 << 24);
+        const uint32_t pack_b = v_pf0 | (v_pf1 << 8) | (v_pf2 << 16) | (v_enabl << 24);
+        steady = (iter > 0 && pack_a == prev_a && pack_b == prev_b) ? steady + 1 : 0;
+        prev_a = pack_a; prev_b = pack_b;
+        if (steady < 2) {
+            A26_SB_POKE(0x1Bu, v_grp0, t0 + 3u);
+            A26_SB_POKE(0x1Eu, v_enam1, t0 + 16u);
+            A26_SB_POKE(0x1Du, v_enam0, t0 + t_enam0);
+            A26_SB_POKE(0x1Cu, g1, t0 + t_grp1);
+            A26_SB_POKE(0x0Du, v_pf0, t0 + t_pf0);
+            A26_SB_POKE(0x0Eu, v_pf1, t0 + t_pf1);
+            A26_SB_POKE(0x0Fu, v_pf2, t0 + t_pf2);
+            A26_SB_POKE(0x1Fu, v_enabl, t0 + t_enabl);
+        }
         a = r; x = x2; y = g0; fc = c; fv = v; nv = zv = r;
         cyc = t0 + k;
         cyc += wsync_stall(cyc, cpu_ls);
@@ -148,13 +172,13 @@ __device__ __forceinline__ bool superblock_f58d(Chip &s, const Tables &T, Ram ra
         uint32_t k = 23u + (((q5 & 0xFFu) + y) >> 8) + (((q9 & 0xFFu) + y) >> 8);
         {
             const uint32_t pv = (m2 & 0xF0u) | (m1 & 0x0Fu);
-            if (!poke_quick(s, 0x0Eu, pv)) tia_poke<VERIFY>(s, T, 0x0Eu, pv, t0 + k, cpu_ls, fb);
+            if (!poke_quick(s, 0x0Eu, pv)) tia_poke_changed<VERIFY>(s, T, 0x0Eu, pv, t0 + k, cpu_ls, fb);
         }
         k += 26u + (((q7 & 0xFFu) + y) >> 8) + (((qb & 0xFFu) + y) >> 8);
         scratch = m3 & 0x0Fu;
         {
             const uint32_t pv = ((m4 & 0xF0u) | scratch) & r90;
-            if (!poke_quick(s, 0x0Eu, pv)) tia_poke<VERIFY>(s, T, 0x0Eu, pv, t0 + k, cpu_ls, fb);
+            if (!poke_quick(s, 0x0Eu, pv)) tia_poke_changed<VERIFY>(s, T, 0x0Eu, pv, t0 + k, cpu_ls, fb);
         }
         // TXA ; INX ; AND #$03 ; BNE
         a = x & 3u; x = (x + 1u) & 0xFFu; nv = zv = a;

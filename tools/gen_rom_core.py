@@ -269,7 +269,7 @@ class Gen:
             if reg == 0x02:                      # WSYNC: park until the end of the scanline, leave the block
                 e(f"cyc += {cyc}u; cyc += wsync_stall(cyc, cpu_ls); pc = 0x{nxt:04X}u; goto a26_next_;")
                 return True
-            e(f"if (!poke_quick(s, 0x{reg:02X}u, {val})) stall_ = tia_poke<VERIFY>(s, T, 0x{reg:02X}u, {val}, cyc + {cyc}u, cpu_ls, fb);")
+            e(f"if (!poke_quick(s, 0x{reg:02X}u, {val})) tia_poke_changed<VERIFY>(s, T, 0x{reg:02X}u, {val}, cyc + {cyc}u, cpu_ls, fb);")
             e(f"cyc += {cyc}u + stall_;")
             if reg == 0x00:
                 e(f"if (s.frame_done) {{ done = 1; pc = 0x{nxt:04X}u; goto a26_next_; }}")
