@@ -31,6 +31,13 @@ enum : int { ERR_UNTRANSLATED = 4 };
 #undef A26_COMPILED_BLOCKMAP
 
 inline void fill_blockmap(uint16_t *dst) { for (int i = 0; i < 2048; ++i) dst[i] = kCompiledBlockMap[i]; }
+// the translated core (and its super-blocks) is only valid for the cartridge it was generated from
+inline bool rom_matches_translation(const uint8_t *rom)
+{
+    uint32_t h = 0x811C9DC5u;
+    for (int i = 0; i < 2048; ++i) h = (h ^ rom[i]) * 0x01000193u;
+    return h == kCompiledRomFnv1a;
+}
 
 #ifdef __CUDACC__
 

@@ -251,6 +251,7 @@ extern "C" int ngp_create(const ngp_config *cfg, const uint8_t *rom, int32_t dev
     h->shape.bias = cfg->bias;
     NGP_CUDA(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
 
+    h->rom_translated = a26::rom_matches_translation(rom) ? 1 : 0;
     Tables tables;
     ngp_host::build_tables(tables, rom, cfg->ball_colour, cfg->left_colour, cfg->right_colour, ngp_ntsc_palette);
     std::vector<uint32_t> needed(a26::TRIGMAX + 1);
@@ -318,6 +319,10 @@ extern "C" int ngp_env_step_core(ngp_handle *h, int32_t core, const uint8_t *act
     NGP_REQUIRE(h && actions, "ngp_env_step: bad arguments");
     NGP_REQUIRE(h->n_envs > 0, "ngp_env_step: call ngp_env_reset first");
     NGP_REQUIRE((loc == nullptr) == (valid == nullptr), "ngp_env_step: loc and valid go together");
+    if (core && !h->rom_translated) {
+        ngp_set_error("ngp_env_step: the statically translated core was generated from a different cartridge; use NGP_CORE_INTERPRETER");
+        return NGP_ERR_UNSUPPORTED;
+    }
     NGP_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int n = h->n_envs;
@@ -382,6 +387,10 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
     p.genomes = genomes; p.hof_genomes = hof_genomes; p.hof_fitness = hof_fitness; p.hof_pick = hof_pick;
     p.n = n; p.n_hof = n_hof; p.G = h->gene_size; p.games = games; p.schedule = h->cfg.schedule;
     p.core = h->cfg.core ? 1 : 0;
+    if (p.core && !h->rom_translated) {
+        ngp_set_error("ngp_evaluate: the statically translated core was generated from a different cartridge; use NGP_CORE_INTERPRETER");
+        return NGP_ERR_UNSUPPORTED;
+    }
     p.win_score = h->cfg.win_score; p.timeout_thresh = h->cfg.timeout_thresh; p.max_frames = h->cfg.max_frames;
     p.time_scaler = (double)h->cfg.time_scaler; p.paddle_height = (double)h->cfg.scaled_paddle_height;
     p.seed = seed; p.generation = generation; p.shape = h->shape;
@@ -392,8 +401,8 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
     int block = 32;
     long long warps = (total + 31) / 32;
     if (p.core) {
-        if (total >= 73728) block = 512;
-        else if (total >= 36864) block = 256;
+        if (total >= 49152) block = 512;               // the largest CTA that still gives ~96 CTAs (measured at 12288 / 24576 / 49152
+        else if (total >= 24576) block = 256;          // environments: profiles/README.md)
         else if (total >= 12288) block = 128;
     } else if (warps > (long long)h->sm_count * 16) block = 128;
     // tuning overrides (experiments only)

@@ -17,6 +17,7 @@ struct ngp_handle {
     int sm_count;
     int gene_size;
     pol::Shape shape;
+    int rom_translated;           // the ROM is the cartridge the statically translated core was generated from
     // device tables
     a26::Tables *d_tables;        // rom + decode + colour-match weights
     uint32_t *d_needed;           // paddle charge -> cycles table [4097]

@@ -280,11 +280,13 @@ __global__ void __launch_bounds__(256) mlp_layer_kernel(const float *__restrict_
 // Thread = one output unit with its weight row in registers, the genome's input rows in shared memory (broadcast
 // reads), stores coalesced along the outputs.  Same accumulation order as mlp_layer_kernel (k ascending, bias last).
 constexpr int NARROW_K = 8;
+template <int NI>        // NI = compile-time fan-in (6: the observation vector), or 0 = run-time fan-in up to NARROW_K - bias
 __global__ void __launch_bounds__(128) mlp_narrow_in_kernel(const float *__restrict__ genomes, size_t w_off, int G, const float *__restrict__ in,
-                                                            int envs, int ni, int no, int bias, float *__restrict__ outp)
+                                                            int envs, int ni_rt, int no, int bias, float *__restrict__ outp)
 {
     constexpr int TE = 64;
     __shared__ float xs[TE * NARROW_K];
+    const int ni = NI ? NI : ni_rt;
     const int g = blockIdx.z, e0 = blockIdx.y * TE, o = blockIdx.x * 128 + threadIdx.x;
     const int K = ni + bias, ne = min(TE, envs - e0);
     const float *src = in + ((size_t)g * envs + e0) * ni;
@@ -301,13 +303,16 @@ __global__ void __launch_bounds__(128) mlp_narrow_in_kernel(const float *__restr
     __syncthreads();
     if (o >= no) return;
     float *dst = outp + ((size_t)g * envs + e0) * no + o;
+#pragma unroll 4
     for (int e = 0; e < ne; ++e) {
+        const float *xe = xs + e * ni;
         float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < NARROW_K; ++k) if (k < ni) acc = fmaf(xs[e * ni + k], w[k], acc);
+        for (int k = 0; k < (NI ? NI : NARROW_K); ++k) if (NI || k < ni) acc = fmaf(xe[k], w[k], acc);
         if (bias) acc = fmaf(1.0f, wb, acc);
-        // fast exponential (ex2.approx) + IEEE reciprocal, as in the tensor-core layer's epilogue: far inside the 1e-5 bar
-        dst[(size_t)e * no] = __frcp_rn(1.0f + __expf(-acc));
+        // fast exponential and reciprocal (ex2.approx, rcp.approx: a few ulp), far inside the 1e-5 bar
+        *dst = __fdividef(1.0f, 1.0f + __expf(-acc));
+        dst += no;
     }
 }
 
@@ -497,7 +502,8 @@ extern "C" int ngp_mlp_forward(ngp_handle *h, const float *genomes, const float 
         }
         if (l != L - 1 && ni + bias <= NARROW_K) {
             dim3 g3((no + 127) / 128, (envs + 63) / 64, n_genomes);
-            mlp_narrow_in_kernel<<<g3, 128, 0, st>>>(genomes, w_off, h->gene_size, in, envs, ni, no, bias, bufs[l & 1]);
+            if (ni == 6) mlp_narrow_in_kernel<6><<<g3, 128, 0, st>>>(genomes, w_off, h->gene_size, in, envs, ni, no, bias, bufs[l & 1]);
+            else mlp_narrow_in_kernel<0><<<g3, 128, 0, st>>>(genomes, w_off, h->gene_size, in, envs, ni, no, bias, bufs[l & 1]);
             h->launches++;
             NGP_CUDA(cudaGetLastError());
             launched = true;

@@ -32,7 +32,7 @@ def _stream(device) -> ctypes.c_void_p:
 
 
 class Engine:
-    def __init__(self, config: Config | None = None, device: int | None = None):
+    def __init__(self, config: Config | None = None, device: int | None = None, rom: bytes | None = None):
         if not torch.cuda.is_available():
             raise _lib.NgpError("no CUDA device: this package has no CPU fallback")
         self.config = config or Config()
@@ -44,7 +44,10 @@ class Engine:
             torch.zeros(1, device=self.device)            # make sure the primary context exists
             h = ctypes.c_void_p()
             cfg = self.config.to_c()
-            _lib.check(self._L.ngp_create(ctypes.byref(cfg), load_rom(), self.device_index, ctypes.byref(h)), "ngp_create")
+            image = load_rom() if rom is None else bytes(rom)      # another 2 KiB cartridge: interpreter core only
+            if len(image) != 2048:
+                raise _lib.NgpError("cartridge image must be 2048 bytes")
+            _lib.check(self._L.ngp_create(ctypes.byref(cfg), image, self.device_index, ctypes.byref(h)), "ngp_create")
         self._h = h
         self.gene_size = int(self._L.ngp_gene_size(self._h))
         self._n_envs = 0

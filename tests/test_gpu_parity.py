@@ -348,3 +348,20 @@ def test_mlp_forward_tensor_core_path(ngp, nodes, envs):
     np.testing.assert_allclose(out_f.cpu().numpy(), ref_out, rtol=1e-5, atol=1e-7)
     assert np.array_equal(act.cpu().numpy(), ref_act) and np.array_equal(act_f.cpu().numpy(), ref_act)
     eng.close()
+
+
+def test_translated_core_refuses_another_cartridge(ngp):
+    """The statically translated 6507 core and its super-blocks are generated from the bundled cartridge; a different
+    2 KiB image must be refused on that path (error, not silently wrong frames) while the interpreter core still runs it."""
+    from neuro_genetic_pong_self_play_b200.engine import load_rom
+    rom = bytearray(load_rom())
+    rom[0x7F0] ^= 0xFF                                   # a byte of padding: never executed by the cartridge's code
+    eng = ngp.Engine(ngp.Config(SCHEDULE=ngp.SCHEDULE_ROUND_ROBIN, POPULATION_SIZE=2, MAX_FRAMES=5), device=0, rom=bytes(rom))
+    g = eng.init_population(2, seed=1)
+    with pytest.raises(ngp.NgpError):
+        eng.evaluate(g, seed=1)
+    eng.close()
+    eng = ngp.Engine(ngp.Config(SCHEDULE=ngp.SCHEDULE_ROUND_ROBIN, POPULATION_SIZE=2, MAX_FRAMES=5, CORE=ngp.CORE_INTERPRETER), device=0, rom=bytes(rom))
+    out = eng.evaluate(eng.init_population(2, seed=1), seed=1)
+    assert int(out["frames_total"]) == 2 * 6 * 5
+    eng.close()

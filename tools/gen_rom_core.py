@@ -435,6 +435,10 @@ class Gen:
         for i in range(0, 2048, 16):
             self.out.append("    " + ", ".join(str(v) for v in blockmap[i:i + 16]) + ",")
         self.out.append("};")
+        fnv = 0x811C9DC5
+        for b in self.rom:
+            fnv = ((fnv ^ b) * 0x01000193) & 0xFFFFFFFF
+        self.out.append(f"static const uint32_t kCompiledRomFnv1a = 0x{fnv:08X}u;   // FNV-1a of the 2 KiB image this file was generated from")
         self.out.append("#else")
         prev_fell_through = False
         self.open_regions = []
