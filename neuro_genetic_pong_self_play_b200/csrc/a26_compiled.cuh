@@ -15,15 +15,18 @@ namespace a26 {
 
 enum : int { ERR_UNTRANSLATED = 4 };
 
-// hooks emitted by the generator at the head of dispatch entries $F621 and $F58D (pong_superblocks.cuh)
+// hooks emitted by the generator at the head of dispatch entries $F621, $F58D and $F5CC (pong_superblocks.cuh)
 #ifndef A26_NO_SUPERBLOCKS
 #define A26_SUPERBLOCK_F621 \
     if (superblock_f621<VERIFY>(s, T, ram, fb, a, x, y, sp, pc, fc, fv, nv, zv, fid, cyc, cpu_ls, sb_iters)) { A26_STAT(6); goto a26_next_; }
 #define A26_SUPERBLOCK_F58D \
     if (superblock_f58d<VERIFY>(s, T, ram, fb, a, x, y, pc, fc, nv, zv, cyc, cpu_ls, sb_iters)) { A26_STAT(7); goto a26_next_; }
+#define A26_SUPERBLOCK_F5CC \
+    if (superblock_f5cc<VERIFY>(s, T, fb, a, y, pc, nv, zv, cyc, cpu_ls, sb_iters)) { A26_STAT(8); goto a26_next_; }
 #else
 #define A26_SUPERBLOCK_F621
 #define A26_SUPERBLOCK_F58D
+#define A26_SUPERBLOCK_F5CC
 #endif
 
 #define A26_COMPILED_BLOCKMAP
@@ -97,7 +100,7 @@ __device__ __forceinline__ void run_frame_compiled(Chip &s, CpuRegs &r, const Ta
         // still inside its frame stands at the loop entry: environments in different game phases reach the loop a few
         // slots apart, and a lane that ran ahead alone would execute the whole loop a second time for the others.
         // (Only a scheduling hint: any iteration count gives the same machine state.)
-        const int sb_iters = __all_sync(__activemask(), done || pc == 0xF621u || pc == 0xF58Du) ? 128 : 1;
+        const int sb_iters = __all_sync(__activemask(), done || pc == 0xF621u || pc == 0xF58Du || pc == 0xF5CCu) ? 128 : 1;
         (void)sb_iters;
         if (!done) {
             if ((cyc - start_cyc) >= FRAME_CYCLE_CAP) done = 1;

@@ -203,5 +203,32 @@ __device__ __forceinline__ bool superblock_f58d(Chip &s, const Tables &T, Ram ra
     return true;
 }
 
+// The blank-line loop $F5B8-$F5CD, entered at $F5CC (the instruction after `STY WSYNC`): 12 scanlines per frame that write
+// zero to PF0-2, GRP0/1, ENAM0/1 and ENABL and wait for the next line.
+//   $F5CC DEY ; BNE $F5B8      $F5B8 LDA #$00 ; STA PF0 ; STA PF1 ; STA PF2 ; STA GRP0 ; STA GRP1 ; STA ENAM0 ; STA ENAM1 ; STA ENABL ; STY WSYNC
+// From the third identical iteration of one call on, the latches are at the fixed point of the write sequence (see
+// superblock_f621) and the writes are skipped.  Leaves with pc = $F5CF (Y reached 0) or $F5CC.
+template <bool VERIFY>
+__device__ __forceinline__ bool superblock_f5cc(Chip &s, const Tables &T, uint8_t *fb, uint32_t &a, uint32_t &y, uint32_t &pc, uint32_t &nv,
+                                                uint32_t &zv, uint32_t &cyc, uint32_t cpu_ls, int max_iters)
+{
+    for (int iter = 0; iter < max_iters; ++iter) {
+        const uint32_t t0 = cyc;
+        y = (y - 1u) & 0xFFu;                              // DEY
+        if (y == 0u) { nv = zv = 0u; cyc = t0 + 4u; pc = 0xF5CFu; return true; }
+        a = 0u; nv = zv = 0u;                              // taken branch (3), LDA #$00 (2)
+        if (iter < 2) {
+            const uint32_t regs[8] = {0x0Du, 0x0Eu, 0x0Fu, 0x1Bu, 0x1Cu, 0x1Du, 0x1Eu, 0x1Fu};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (!poke_quick(s, regs[i], 0u)) tia_poke_changed<VERIFY>(s, T, regs[i], 0u, t0 + 10u + 3u * (uint32_t)i, cpu_ls, fb);
+        }
+        cyc = t0 + 34u;                                    // 2 + 3 + 2 + 8 * 3 + 3 (STY WSYNC)
+        cyc += wsync_stall(cyc, cpu_ls);
+    }
+    pc = 0xF5CCu;
+    return true;
+}
+
 #endif  // __CUDACC__
 }  // namespace a26

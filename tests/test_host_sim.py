@@ -138,7 +138,7 @@ def test_superblocks_are_taken():
     for i in range(16):
         st[i] = 0
     _run_fast_against_oracle(L, sim, frames, seed=3)
-    assert st[6] >= frames and st[7] >= frames, (st[6], st[7])
+    assert st[6] >= frames and st[7] >= frames and st[8] >= frames, (st[6], st[7], st[8])
     assert st[5] < 100 * frames, st[5]
 
 

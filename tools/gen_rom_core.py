@@ -32,12 +32,13 @@ BRANCH = {"BPL": ("((nv >> 7) & 1u)", 0), "BMI": ("((nv >> 7) & 1u)", 1), "BVC":
 PAGE_PENALTY = {"abx", "aby", "izy"}          # only for read instructions
 MAX_STRUCTURED_SKIP = 24                      # bytes a structured forward branch may skip
 # dispatch entries tried first, hottest first (dispatches per frame measured with tests/host_sim + A26_STATS)
-HOT_ENTRIES = [0xF621, 0xF58D, 0xF58B, 0xF5CC, 0xF5B8, 0xF21F, 0xF094]
+HOT_ENTRIES = [0xF5CC, 0xF438, 0xF457, 0xF455, 0xF445]      # with the super-blocks in place (80 dispatches per frame)
 # Hand-fused super-blocks (csrc/pong_superblocks.cuh): dispatch entry -> (first byte, last byte + 1, sha1 of the cartridge
 # bytes the fused code was written against).  The hook is only emitted when the ROM still holds exactly those bytes.
 SUPERBLOCKS = {0xF621: (0xF5E0, 0xF63E, "9cf83bee22051baf07f26f6b6fd104e7b6f90ebe"),
-               0xF58D: (0xF58B, 0xF5B6, "2c60768c1cb396d94451a9af3be5bc39cdc01337")}
-SUPERBLOCK_EXITS = [0xF63E, 0xF5B6]          # program counters a super-block can leave with: must be dispatch entries
+               0xF58D: (0xF58B, 0xF5B6, "2c60768c1cb396d94451a9af3be5bc39cdc01337"),
+               0xF5CC: (0xF5B8, 0xF5CF, "f66582c70f16bda072d1617e078b396fbd1f594b")}
+SUPERBLOCK_EXITS = [0xF63E, 0xF5B6, 0xF5CF]          # program counters a super-block can leave with: must be dispatch entries
 
 
 def load_rom():
