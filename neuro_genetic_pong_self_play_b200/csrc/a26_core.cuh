@@ -634,13 +634,27 @@ __device__ __forceinline__ bool poke_quick(Chip &s, uint32_t reg, uint32_t v)
     case 0x0D: A26_QUICK(pf0, 0xF0);
     case 0x0E: return v == s.pf1;
     case 0x0F: return v == s.pf2;
-    case 0x1B: return v == s.grp0_new && s.grp1_old == s.grp1_new;
-    case 0x1C:
-        if (v == s.grp1_new && s.grp0_old == s.grp0_new && ((s.enabl_old ^ s.enabl_new) & 2) == 0) { s.enabl_old = s.enabl_new; return true; }
+    // GRP0 shows its new latch unless VDELP0 is set, GRP1 shows its old latch only when VDELP1 is set (and likewise the ball
+    // with VDELBL): a write whose direct effect and whose old<-new copies touch nothing that is currently displayed is applied
+    // to the latches right here.
+    case 0x1B:
+        if (((s.vdelp0 & 1) || v == s.grp0_new) && (!(s.vdelp1 & 1) || s.grp1_old == s.grp1_new)) {
+            s.grp0_new = (uint8_t)v; s.grp1_old = s.grp1_new;
+            return true;
+        }
         return false;
-    case 0x1D: A26_QUICK(enam0, 0x02);
-    case 0x1E: A26_QUICK(enam1, 0x02);
-    case 0x1F: A26_QUICK(enabl_new, 0x02);
+    case 0x1C:
+        if (((s.vdelp1 & 1) || v == s.grp1_new) && (!(s.vdelp0 & 1) || s.grp0_old == s.grp0_new) &&
+            (!(s.vdelbl & 1) || ((s.enabl_old ^ s.enabl_new) & 2) == 0)) {
+            s.grp1_new = (uint8_t)v; s.grp0_old = s.grp0_new; s.enabl_old = s.enabl_new;
+            return true;
+        }
+        return false;
+    // a missile locked to its player (RESMPx.D1) is hidden whatever its enable bit says: the bit is unobservable until the lock
+    // is released (a RESMPx write, which goes the long way)
+    case 0x1D: if (s.resmp0 & 2) { s.enam0 = (uint8_t)v; return true; } A26_QUICK(enam0, 0x02);
+    case 0x1E: if (s.resmp1 & 2) { s.enam1 = (uint8_t)v; return true; } A26_QUICK(enam1, 0x02);
+    case 0x1F: if (s.vdelbl & 1) { s.enabl_new = (uint8_t)v; return true; } A26_QUICK(enabl_new, 0x02);   // delayed ball shows the old latch
     case 0x20: s.hmp0 = (uint8_t)v; return true;
     case 0x21: s.hmp1 = (uint8_t)v; return true;
     case 0x22: s.hmm0 = (uint8_t)v; return true;
@@ -663,6 +677,32 @@ __device__ __forceinline__ uint32_t wsync_stall(uint32_t cyc_after, uint32_t cpu
     return c ? LINE_CYCLES - c : 0u;
 }
 
+// Fused mode, playfield / colour registers while no movable object is enabled: nothing can collide, and rows outside the crop
+// add nothing to the observation whatever the registers hold.  When everything between the renderer's position and this
+// write lies above the crop (score area) or below it, the renderer is left where it is (it will cross those rows later with
+// the new values, to the same effect: none) and only the latch changes.  Returns true when the write has been handled.
+__device__ __forceinline__ bool tia_latch_only(Chip &s, uint32_t reg, uint32_t v, uint32_t cyc_after)
+{
+    if (!(reg >= 0x06 && reg <= 0x0F && reg != 0x0B && reg != 0x0C)) return false;
+    const int crop_first = YSTART + CROP_TOP, crop_end = YSTART + CROP_BOTTOM;     // TIA lines of the crop
+    const bool above = s.line < crop_first &&
+                       (int32_t)(cyc_after + 4u - (s.tia_ls + (uint32_t)(crop_first - s.line) * LINE_CYCLES)) < 0;   // +4: write delay
+    const bool below = s.line >= crop_end && !s.frame_done;
+    if (!(above || below)) return false;
+    if ((s.grp0_new | s.grp0_old | s.grp1_new | s.grp1_old) != 0 || ((s.enam0 | s.enam1 | s.enabl_new | s.enabl_old) & 2) != 0) return false;
+    switch (reg) {
+    case 0x06: s.colup0 = (uint8_t)v; break;
+    case 0x07: s.colup1 = (uint8_t)v; break;
+    case 0x08: s.colupf = (uint8_t)v; break;
+    case 0x09: s.colubk = (uint8_t)v; break;
+    case 0x0A: s.ctrlpf = (uint8_t)v; s.pf_dirty = 1; break;
+    case 0x0D: s.pf0 = (uint8_t)v; s.pf_dirty = 1; break;
+    case 0x0E: s.pf1 = (uint8_t)v; s.pf_dirty = 1; break;
+    default: s.pf2 = (uint8_t)v; s.pf_dirty = 1; break;
+    }
+    return true;
+}
+
 // Apply one TIA register write at its exact time: bring the lazy renderer up to the write's colour clock
 // (plus the register's delay), then change the latch.  cil = CPU cycle within the scanline after the write.
 template <bool VERIFY>
@@ -670,30 +710,7 @@ __device__ __forceinline__ void tia_apply(Chip &s, const Tables &T, uint32_t reg
 {
     A26_STAT(1);
     A26_STAT_REG(reg);
-    if (!VERIFY && reg >= 0x06 && reg <= 0x0F && reg != 0x0B && reg != 0x0C) {
-        // Fused mode, playfield / colour registers while no movable object is enabled: nothing can collide, and rows outside
-        // the crop add nothing to the observation whatever the registers hold.  When everything between the renderer's
-        // position and this write lies above the crop (score area) or below it, the renderer is left where it is (it will
-        // cross those rows later with the new values, to the same effect: none) and only the latch changes.
-        const int crop_first = YSTART + CROP_TOP, crop_end = YSTART + CROP_BOTTOM;     // TIA lines of the crop
-        const bool above = s.line < crop_first &&
-                           (int32_t)(cyc_after + 4u - (s.tia_ls + (uint32_t)(crop_first - s.line) * LINE_CYCLES)) < 0;   // +4: write delay
-        const bool below = s.line >= crop_end && !s.frame_done;
-        const bool objects = (s.grp0_new | s.grp0_old | s.grp1_new | s.grp1_old) != 0 || ((s.enam0 | s.enam1 | s.enabl_new | s.enabl_old) & 2) != 0;
-        if ((above || below) && !objects) {
-            switch (reg) {
-            case 0x06: s.colup0 = (uint8_t)v; break;
-            case 0x07: s.colup1 = (uint8_t)v; break;
-            case 0x08: s.colupf = (uint8_t)v; break;
-            case 0x09: s.colubk = (uint8_t)v; break;
-            case 0x0A: s.ctrlpf = (uint8_t)v; s.pf_dirty = 1; break;
-            case 0x0D: s.pf0 = (uint8_t)v; s.pf_dirty = 1; break;
-            case 0x0E: s.pf1 = (uint8_t)v; s.pf_dirty = 1; break;
-            default: s.pf2 = (uint8_t)v; s.pf_dirty = 1; break;
-            }
-            return;
-        }
-    }
+    if (!VERIFY && tia_latch_only(s, reg, v, cyc_after)) return;
     const int hpos = 3 * (int)cil;
     int delay = 0;
     switch (reg) {

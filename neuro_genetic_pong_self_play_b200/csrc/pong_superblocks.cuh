@@ -172,13 +172,13 @@ __device__ __forceinline__ bool superblock_f58d(Chip &s, const Tables &T, Ram ra
         uint32_t k = 23u + (((q5 & 0xFFu) + y) >> 8) + (((q9 & 0xFFu) + y) >> 8);
         {
             const uint32_t pv = (m2 & 0xF0u) | (m1 & 0x0Fu);
-            if (!poke_quick(s, 0x0Eu, pv)) tia_poke_changed<VERIFY>(s, T, 0x0Eu, pv, t0 + k, cpu_ls, fb);
+            if (!poke_quick(s, 0x0Eu, pv) && (VERIFY || !tia_latch_only(s, 0x0Eu, pv, t0 + k))) tia_poke_changed<VERIFY>(s, T, 0x0Eu, pv, t0 + k, cpu_ls, fb);
         }
         k += 26u + (((q7 & 0xFFu) + y) >> 8) + (((qb & 0xFFu) + y) >> 8);
         scratch = m3 & 0x0Fu;
         {
             const uint32_t pv = ((m4 & 0xF0u) | scratch) & r90;
-            if (!poke_quick(s, 0x0Eu, pv)) tia_poke_changed<VERIFY>(s, T, 0x0Eu, pv, t0 + k, cpu_ls, fb);
+            if (!poke_quick(s, 0x0Eu, pv) && (VERIFY || !tia_latch_only(s, 0x0Eu, pv, t0 + k))) tia_poke_changed<VERIFY>(s, T, 0x0Eu, pv, t0 + k, cpu_ls, fb);
         }
         // TXA ; INX ; AND #$03 ; BNE
         a = x & 3u; x = (x + 1u) & 0xFFu; nv = zv = a;
