@@ -67,6 +67,7 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
     // one of the eight writes would find its latch unchanged, so they are skipped without reading the latches.
     uint32_t prev_a = 0, prev_b = 0;
     int steady = 0;
+    uint32_t pf_row = 0xFFFFFFFFu, v_pf0 = 0, v_pf1 = 0, v_pf2 = 0, pf_cross = 0;     // playfield bytes of the current table row
     // bounded by the caller (at most one trip of X through its 8-bit range), then back through the dispatcher
     for (int iter = 0; iter < max_iters; ++iter) {
         const uint32_t x1 = (x + 1u) & 0xFFu, x2 = (x + 2u) & 0xFFu;
@@ -108,12 +109,17 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
         const uint32_t t_grp1 = k;
         // ---- TXA ; LSR ; LSR ; LSR ; TAY ; LDA ($9B),Y ; STA PF0 ; LDA ($9D),Y ; STA PF1 ; LDA ($9F),Y ; STA PF2 ----
         k += 10u;
-        k += 8u + (((p0 & 0xFFu) + row) >> 8);
-        const uint32_t t_pf0 = k, v_pf0 = rom_byte(T, p0 + row);
-        k += 8u + (((p1 & 0xFFu) + row) >> 8);
-        const uint32_t t_pf1 = k, v_pf1 = rom_byte(T, p1 + row);
-        k += 8u + (((p2 & 0xFFu) + row) >> 8);
-        const uint32_t t_pf2 = k, v_pf2 = rom_byte(T, p2 + row);
+        if (row != pf_row) {                                            // the table row changes every fourth iteration
+            pf_row = row;
+            v_pf0 = rom_byte(T, p0 + row); v_pf1 = rom_byte(T, p1 + row); v_pf2 = rom_byte(T, p2 + row);
+            pf_cross = (((p0 & 0xFFu) + row) >> 8) | ((((p1 & 0xFFu) + row) >> 8) << 1) | ((((p2 & 0xFFu) + row) >> 8) << 2);   // page crossings
+        }
+        k += 8u + (pf_cross & 1u);
+        const uint32_t t_pf0 = k;
+        k += 8u + ((pf_cross >> 1) & 1u);
+        const uint32_t t_pf1 = k;
+        k += 8u + (pf_cross >> 2);
+        const uint32_t t_pf2 = k;
         // ---- INX ; TXA ; LDX #$1F ; TXS ; TAX ; LDY #$F0 ; SEC ; SBC $B2 ; AND $A5 ; BEQ ; LDY #$00 ----
         const uint32_t g0 = (((x2 - b2) & a5) & 0xFFu) == 0u ? 0xF0u : 0x00u;
         k += 20u + (g0 ? 3u : 4u);
