@@ -399,19 +399,16 @@ __device__ __forceinline__ bool render_parts_quick(Chip &s, const Tables &T, con
         const uint32_t wts = T.weight[o[i].colour >> 1];
         if (!wts) continue;
         uint32_t n_r = 0, sx_r = 0, n_y = 0;             // pixels x rows, column sums x rows, pixels x row-index sums
-        const int os = o[i].start, oe = os + o[i].width;
-        const uint32_t n_full = __popc(o[i].pat), sx_full = n_full * (uint32_t)os + bit_index_sum(o[i].pat);
 #pragma unroll
         for (int p = 0; p < NPARTS; ++p) {
-            if (!nrows[p] || part[p].x1 <= os || oe <= part[p].x0) continue;
-            uint32_t n = n_full, sx = sx_full;
-            if (part[p].x0 > os || oe > part[p].x1) {     // the rectangle's edge cuts through the object (rare)
-                int lo = part[p].x0 - os, hi = part[p].x1 - os;
-                lo = lo < 0 ? 0 : lo; hi = hi > o[i].width ? o[i].width : hi;
-                const uint32_t clip = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-                const uint32_t q = o[i].pat & clip;
-                n = __popc(q); sx = n * (uint32_t)os + bit_index_sum(q);
-            }
+            if (!nrows[p]) continue;
+            int lo = part[p].x0 - o[i].start, hi = part[p].x1 - o[i].start;
+            lo = lo < 0 ? 0 : lo; hi = hi > o[i].width ? o[i].width : hi;
+            if (hi <= lo) continue;
+            const uint32_t clip = (hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+            const uint32_t q = o[i].pat & clip;
+            if (!q) continue;
+            const uint32_t n = __popc(q), sx = n * (uint32_t)o[i].start + bit_index_sum(q);
             n_r += n * nrows[p]; sx_r += sx * nrows[p]; n_y += n * rowsum[p];
         }
         if (!n_r) continue;

@@ -64,10 +64,11 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
     const uint32_t dump_cyc = s.dump_cyc, need0 = s.needed[sel], need1 = s.needed[2u + sel];
     // Steady state: when an iteration writes the same eight bytes as the two before it (inside this call), the latches
     // -- including the old/new copies that GRP0/GRP1 writes shuffle -- are at the fixed point of that write sequence: every
-    // one of the eight writes would find its latch unchanged, so they are skipped without reading the latches.
+    // one of the eight writes would find its latch unchanged, so they are skipped without reading the latches.  (Testing the
+    // five plain latches byte by byte against the previous iteration instead was measured slower: eight branches per
+    // iteration cost more than the latch reads they save.)
     uint32_t prev_a = 0, prev_b = 0;
     int steady = 0;
-    uint32_t pf_row = 0xFFFFFFFFu, v_pf0 = 0, v_pf1 = 0, v_pf2 = 0, pf_cross = 0;     // playfield bytes of the current table row
     // bounded by the caller (at most one trip of X through its 8-bit range), then back through the dispatcher
     for (int iter = 0; iter < max_iters; ++iter) {
         const uint32_t x1 = (x + 1u) & 0xFFu, x2 = (x + 2u) & 0xFFu;
@@ -109,17 +110,12 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
         const uint32_t t_grp1 = k;
         // ---- TXA ; LSR ; LSR ; LSR ; TAY ; LDA ($9B),Y ; STA PF0 ; LDA ($9D),Y ; STA PF1 ; LDA ($9F),Y ; STA PF2 ----
         k += 10u;
-        if (row != pf_row) {                                            // the table row changes every fourth iteration
-            pf_row = row;
-            v_pf0 = rom_byte(T, p0 + row); v_pf1 = rom_byte(T, p1 + row); v_pf2 = rom_byte(T, p2 + row);
-            pf_cross = (((p0 & 0xFFu) + row) >> 8) | ((((p1 & 0xFFu) + row) >> 8) << 1) | ((((p2 & 0xFFu) + row) >> 8) << 2);   // page crossings
-        }
-        k += 8u + (pf_cross & 1u);
-        const uint32_t t_pf0 = k;
-        k += 8u + ((pf_cross >> 1) & 1u);
-        const uint32_t t_pf1 = k;
-        k += 8u + (pf_cross >> 2);
-        const uint32_t t_pf2 = k;
+        k += 8u + (((p0 & 0xFFu) + row) >> 8);
+        const uint32_t t_pf0 = k, v_pf0 = rom_byte(T, p0 + row);
+        k += 8u + (((p1 & 0xFFu) + row) >> 8);
+        const uint32_t t_pf1 = k, v_pf1 = rom_byte(T, p1 + row);
+        k += 8u + (((p2 & 0xFFu) + row) >> 8);
+        const uint32_t t_pf2 = k, v_pf2 = rom_byte(T, p2 + row);
         // ---- INX ; TXA ; LDX #$1F ; TXS ; TAX ; LDY #$F0 ; SEC ; SBC $B2 ; AND $A5 ; BEQ ; LDY #$00 ----
         const uint32_t g0 = (((x2 - b2) & a5) & 0xFFu) == 0u ? 0xF0u : 0x00u;
         k += 20u + (g0 ? 3u : 4u);
@@ -172,20 +168,31 @@ __device__ __forceinline__ bool superblock_f58d(Chip &s, const Tables &T, Ram ra
     if (y >= 5u || !(q5 & q7 & q9 & qb & (q5 + 4u) & (q7 + 4u) & (q9 + 4u) & (qb + 4u) & 0x1000u)) return false;
     const uint32_t r90 = ram.rd(0x90u);
     uint32_t scratch = 0;
+    // The score lines lie above the crop and no movable object is enabled there: PF1 changes are latch-only (tia_latch_only).
+    // The renderer position and the object latches only change when a write does go the long way, so the test is evaluated
+    // once and after such a write; per write it is a comparison of its cycle stamp with the crop's first cycle.
+    bool quiet_zone = false;
+    uint32_t zone_end = 0;
+    auto refresh_zone = [&]() {
+        quiet_zone = !VERIFY && s.line < YSTART + CROP_TOP && (s.grp0_new | s.grp0_old | s.grp1_new | s.grp1_old) == 0 &&
+                     ((s.enam0 | s.enam1 | s.enabl_new | s.enabl_old) & 2) == 0;
+        zone_end = s.tia_ls + (uint32_t)(YSTART + CROP_TOP - s.line) * LINE_CYCLES - 4u;
+    };
+    refresh_zone();
+    auto write_pf1 = [&](uint32_t pv, uint32_t t) {
+        if (poke_quick(s, 0x0Eu, pv)) return;
+        if (quiet_zone && (int32_t)(t - zone_end) < 0) { s.pf1 = (uint8_t)pv; s.pf_dirty = 1; return; }
+        tia_poke_changed<VERIFY>(s, T, 0x0Eu, pv, t, cpu_ls, fb);
+        refresh_zone();
+    };
     for (int iter = 0; iter < max_iters; ++iter) {
         const uint32_t t0 = cyc;
         const uint32_t m1 = rom_byte(T, q5 + y), m2 = rom_byte(T, q9 + y), m3 = rom_byte(T, q7 + y), m4 = rom_byte(T, qb + y);
         uint32_t k = 23u + (((q5 & 0xFFu) + y) >> 8) + (((q9 & 0xFFu) + y) >> 8);
-        {
-            const uint32_t pv = (m2 & 0xF0u) | (m1 & 0x0Fu);
-            if (!poke_quick(s, 0x0Eu, pv) && (VERIFY || !tia_latch_only(s, 0x0Eu, pv, t0 + k))) tia_poke_changed<VERIFY>(s, T, 0x0Eu, pv, t0 + k, cpu_ls, fb);
-        }
+        write_pf1((m2 & 0xF0u) | (m1 & 0x0Fu), t0 + k);
         k += 26u + (((q7 & 0xFFu) + y) >> 8) + (((qb & 0xFFu) + y) >> 8);
         scratch = m3 & 0x0Fu;
-        {
-            const uint32_t pv = ((m4 & 0xF0u) | scratch) & r90;
-            if (!poke_quick(s, 0x0Eu, pv) && (VERIFY || !tia_latch_only(s, 0x0Eu, pv, t0 + k))) tia_poke_changed<VERIFY>(s, T, 0x0Eu, pv, t0 + k, cpu_ls, fb);
-        }
+        write_pf1(((m4 & 0xF0u) | scratch) & r90, t0 + k);
         // TXA ; INX ; AND #$03 ; BNE
         a = x & 3u; x = (x + 1u) & 0xFFu; nv = zv = a;
         k += 6u;

@@ -178,8 +178,9 @@ __device__ __forceinline__ bool episode_frame(Episode &ep, const RolloutParams &
         loc[t][1] = valid[t] ? __ddiv_rn((double)s.sx[t], (double)s.cnt[t]) : 0.0;
     }
     // ---- get_actions (main.py:138-154) ----
-    int left_act = pol::random_action_bit(p.seed, (uint32_t)ep.env, (uint32_t)ep.frame, 0) ? pol::ACT_DOWN : pol::ACT_UP;
-    int right_act = pol::random_action_bit(p.seed, (uint32_t)ep.env, (uint32_t)ep.frame, 1) ? pol::ACT_DOWN : pol::ACT_UP;
+    // the reference draws two random actions every frame (main.py:139-140); with a counter-based generator the draw is a pure
+    // function of (seed, env, frame, player), so it is only evaluated on the one path that uses it
+    int left_act = pol::ACT_NONE, right_act = pol::ACT_NONE;
     if (valid[0]) {
         const double lb[2] = {ep.have_last_ball ? ep.last_ball[0] : loc[0][0], ep.have_last_ball ? ep.last_ball[1] : loc[0][1]};
         // deviation: the reference raises TypeError when one paddle is missing
@@ -188,9 +189,10 @@ __device__ __forceinline__ bool episode_frame(Episode &ep, const RolloutParams &
             const double fball[2] = {loc[0][0], __dsub_rn(160.0, loc[0][1])}, flast[2] = {lb[0], __dsub_rn(160.0, lb[1])};
             left_act = run_policy(p.shape, ep.plan.left_kind, ep.plan.left_genome, fball, flast, loc[1][0], loc[2][0], s1, s2);
             right_act = run_policy(p.shape, pol::KIND_MLP, ep.plan.right_genome, loc[0], lb, loc[2][0], loc[1][0], s1, s2);
+        } else {
+            left_act = pol::random_action_bit(p.seed, (uint32_t)ep.env, (uint32_t)ep.frame, 0) ? pol::ACT_DOWN : pol::ACT_UP;
+            right_act = pol::random_action_bit(p.seed, (uint32_t)ep.env, (uint32_t)ep.frame, 1) ? pol::ACT_DOWN : pol::ACT_UP;
         }
-    } else {
-        left_act = right_act = pol::ACT_NONE;
     }
     ep.have_last_ball = valid[0];
     if (valid[0]) { ep.last_ball[0] = loc[0][0]; ep.last_ball[1] = loc[0][1]; }
