@@ -402,24 +402,27 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
     long long warps = (total + 31) / 32;
     if (p.core && total >= 12288) {
         // measured at 12288 / 24576 / 49152 environments (profiles/README.md): while one CTA per SM is enough, 128- or
-        // 256-thread CTAs with the full register budget; beyond that the largest CTA that still gives ~96 CTAs
+        // 256- / 384-thread CTAs with the largest register budget that fits; beyond that 512-thread CTAs
         if (total <= (long long)h->sm_count * 128) block = 128;
         else if (total <= (long long)h->sm_count * 256) block = 256;
-        else block = total >= 49152 ? 512 : 256;
+        else if (total <= (long long)h->sm_count * 384) block = 384;
+        else block = 512;
     } else if (!p.core && warps > (long long)h->sm_count * 16) block = 128;
     // tuning overrides (experiments only)
     if (const char *e = getenv("NGP_ROLLOUT_BLOCK")) { int b = atoi(e); if (b >= 32 && b <= 1024 && b % 32 == 0) block = b; }
     const bool sync = p.core && block > 32 && !getenv("NGP_ROLLOUT_NOSYNC");
-    // register budget: MAXT=256 lets the compiler have the ~210 registers it wants (no spills: +8 % per warp, measured);
-    // MAXT=512 caps them at 128 (16 warps per SM), MAXT=640 at 96 (20 warps per SM).  While every CTA has an SM to itself
-    // the fat flavour is used; beyond that occupancy is worth more than the spills.
+    // register budget: MAXT=256 lets the compiler have the ~210-230 registers it wants (no spills: +8 % per one-warp CTA, +22 %
+    // for CTA-synchronous launches, measured); MAXT=384 gives 168, MAXT=512 caps them at 128 (16 warps per SM), MAXT=640 at 96.
+    // While every CTA has an SM to itself the fattest flavour that fits the CTA is used; beyond that occupancy is worth more
+    // than the spills.
     long long blocks = (total + block - 1) / block;
-    int lean = sync ? (block <= 256 && blocks <= (long long)h->sm_count ? 0 : 1) : 0;
+    const bool one_per_sm = blocks <= (long long)h->sm_count;
+    int lean = sync ? (one_per_sm && block <= 256 ? 0 : one_per_sm && block <= 384 ? 3 : 1) : 0;
     if (const char *e = getenv("NGP_ROLLOUT_LEAN")) lean = atoi(e);
     if (!sync) lean = 0;
     auto kernel = !p.core ? rollout_kernel<0, false, 384>
                           : (!sync ? rollout_kernel<1, false, 256>
-                                   : (lean == 2 ? rollout_kernel<1, true, 640> : lean == 1 ? rollout_kernel<1, true, 512> : rollout_kernel<1, true, 256>));
+                                   : (lean == 3 ? rollout_kernel<1, true, 384> : lean == 2 ? rollout_kernel<1, true, 640> : lean == 1 ? rollout_kernel<1, true, 512> : rollout_kernel<1, true, 256>));
     const size_t smem = (size_t)block * 32 * 4;
     int per_sm = 0;
     if (smem + sizeof(Tables) > 48 * 1024) NGP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
