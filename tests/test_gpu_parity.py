@@ -365,3 +365,29 @@ def test_translated_core_refuses_another_cartridge(ngp):
     out = eng.evaluate(eng.init_population(2, seed=1), seed=1)
     assert int(out["frames_total"]) == 2 * 6 * 5
     eng.close()
+
+
+def test_find_stuff_kernel_dense_random_frames(engine):
+    """K2 on frames where target bytes are everywhere (every 16-byte vector takes the exact-accounting path, several targets
+    and single-channel matches inside one vector, matches in the first and last vector of a row) and on sparse ones, against
+    the restated find_stuff.  Sums are integers, so the comparison is exact."""
+    import oracle
+    rng = np.random.RandomState(123)
+    cols = np.array([[236, 236, 236], [213, 130, 74], [92, 186, 92], [144, 72, 17], [0, 0, 0]], np.uint8)
+    frames = []
+    for density in (0.9, 0.3, 0.02, 0.0005):
+        f = np.empty((210, 160, 3), np.uint8); f[:] = cols[3]
+        pick = rng.random_sample((210, 160)) < density
+        f[pick] = cols[rng.randint(0, 5, pick.sum())]
+        byte_noise = rng.random_sample((210, 160, 3)) < density * 0.2            # single-channel matches
+        f[byte_noise] = rng.choice(cols[:3].ravel(), byte_noise.sum())
+        frames.append(f)
+    edge = np.zeros((210, 160, 3), np.uint8); edge[34, 0] = cols[0]; edge[193, 159] = cols[1]; edge[100, 5] = cols[2]; edge[33, 7] = cols[0]; edge[194, 9] = cols[2]
+    frames.append(edge)
+    frames = np.stack(frames)
+    loc, valid = engine.find_stuff(torch.from_numpy(frames).cuda())
+    loc = loc.cpu().numpy(); valid = valid.cpu().numpy()
+    for i, f in enumerate(frames):
+        rl, rv = oracle.find_stuff(f)
+        assert np.array_equal(valid[i], rv), i
+        assert np.array_equal(loc[i][rv == 1], rl[rv == 1].astype(np.float32)), i
