@@ -375,7 +375,13 @@ class Gen:
             e("uint32_t stall_ = 0;")
             e(f"A26_WRITE_DYN(0x100u | sp, 0x{ret >> 8:02X}u, cyc + 4u); sp = (sp - 1) & 0xFFu;")
             e(f"A26_WRITE_DYN(0x100u | sp, 0x{ret & 0xFF:02X}u, cyc + 5u); sp = (sp - 1) & 0xFFu;")
-            e(f"pc = 0x{b1 | b2 << 8:04X}u; cyc += 6u + stall_; goto a26_next_;")
+            # straight to the subroutine's block (no trip through the dispatcher; the matching RTS goes through it)
+            t = b1 | b2 << 8
+            if t in self.leaders and t in self.instrs:
+                self.goto_targets.add(t)
+                e(f"cyc += 6u + stall_; if (done) {{ pc = 0x{t:04X}u; goto a26_next_; }} goto L_{t:04X};")
+            else:
+                e(f"pc = 0x{t:04X}u; cyc += 6u + stall_; goto a26_next_;")
             ends = True
         elif mn == "RTS":
             e("sp = (sp + 1) & 0xFFu; const uint32_t lo_ = bus_read<VERIFY>(s, T, ram, 0x100u | sp, cyc, 0u, fb);")
