@@ -358,11 +358,20 @@ class Gen:
                 # backward branch: loop without a trip through the dispatcher
                 self.goto_targets.add(t)
                 e(f"if ({flag} == {want}u) {{ cyc += {taken}u; goto L_{t:04X}; }}")
+            elif t > pc and t in self.leaders and t in self.instrs:
+                # forward branch to another block: straight there (cannot loop, so the dispatcher's cycle cap is not needed)
+                self.goto_targets.add(t)
+                e(f"if ({flag} == {want}u) {{ cyc += {taken}u; goto L_{t:04X}; }}")
             else:
                 e(f"if ({flag} == {want}u) {{ pc = 0x{t:04X}u; cyc += {taken}u; goto a26_next_; }}")
             e("cyc += 2u;")
         elif mn == "JMP" and mode == "abs":
-            e(f"pc = 0x{b1 | b2 << 8:04X}u; cyc += 3u; goto a26_next_;")
+            t = b1 | b2 << 8
+            if t > pc and t in self.leaders and t in self.instrs:
+                self.goto_targets.add(t)
+                e(f"cyc += 3u; goto L_{t:04X};")
+            else:
+                e(f"pc = 0x{t:04X}u; cyc += 3u; goto a26_next_;")
             ends = True
         elif mn == "JMP" and mode == "ind":
             p = b1 | b2 << 8
