@@ -288,6 +288,45 @@ class Gen:
         self.intim_taken = 3 + (1 if (t ^ (nxt + 2)) & 0xFF00 else 0)
         return True
 
+    def closed_form_loop(self, pc, mn, mode, nxt):
+        """Two-/three-instruction register-only loops of the cartridge's positioning routine, replaced by their closed form
+        (exact: registers, flags and cycle count after the loop; nothing inside the loop touches memory or I/O):
+          P: DEY ; BPL P                    -- delay loop
+          P: INY ; SBC #k ; BCS P           -- divide by k
+        The loop's other instructions must not be entered from elsewhere; they are skipped by generate()."""
+        e = self.emit
+        ins = self.instrs
+        def rel_target(a):
+            b1 = ins[a][3]
+            return (a + 2 + (b1 - 256 if b1 > 127 else b1)) & 0xFFFF
+        if mn == "DEY" and nxt in ins and ins[nxt][0] == "BPL" and rel_target(nxt) == pc and nxt not in self.leaders:
+            taken = 3 + (1 if (pc ^ (nxt + 2)) & 0xFF00 else 0)
+            e(f"/* DEY ; BPL {pc:04X}: n iterations in closed form */")
+            e("const uint32_t n_ = (y >= 1u && y <= 0x80u) ? y + 1u : 1u;")
+            e("y = (y - n_) & 0xFFu; nv = zv = y;")
+            e(f"cyc += n_ * 2u + (n_ - 1u) * {taken}u + 2u;")
+            self.skip.add(nxt)
+            return True
+        if mn == "INY" and nxt in ins and ins[nxt][0] == "SBC" and ins[nxt][1] == "imm":
+            br = nxt + 2
+            if br in ins and ins[br][0] == "BCS" and rel_target(br) == pc and nxt not in self.leaders and br not in self.leaders:
+                k = ins[nxt][3]
+                if k > 0:
+                    taken = 3 + (1 if (pc ^ (br + 2)) & 0xFF00 else 0)
+                    e(f"/* INY ; SBC #${k:02X} ; BCS {pc:04X}: closed form (every SBC but the last finds A >= k with carry set) */")
+                    e("y = (y + 1) & 0xFFu;")
+                    e(f"A26_ADC(0x{k ^ 0xFF:02X}u);")
+                    e("cyc += 4u;")
+                    e("if (fc == 1u) {")
+                    e(f"    const uint32_t m_ = a / {k}u;            /* further subtractions that do not borrow */")
+                    e(f"    a -= m_ * {k}u; y = (y + m_ + 1u) & 0xFFu;")
+                    e(f"    A26_ADC(0x{k ^ 0xFF:02X}u);              /* the one that borrows: flags of the loop exit */")
+                    e(f"    cyc += {taken}u + m_ * (4u + {taken}u) + 4u + 2u;")
+                    e("} else cyc += 2u;")
+                    self.skip.add(nxt); self.skip.add(br)
+                    return True
+        return False
+
     def gen_instr(self, pc):
         mn, mode, cyc, b1, b2, n = self.instrs[pc]
         nxt = (pc + n) & 0xFFFF
@@ -296,6 +335,9 @@ class Gen:
         self.out.append(f"  {{ /* {pc:04X}: {raw:<9}{mn} {mode} */")
         self.cur_pc = pc
         ends = False
+        if self.closed_form_loop(pc, mn, mode, nxt):
+            self.out.append("  }")
+            return False
         if mn == "LDA" and mode == "abs" and ((b1 | b2 << 8) & 0x1FFF) == 0x0284 and self.is_intim_wait(pc, nxt):
             # `LDA INTIM; BNE *-3`: skip whole iterations that are known to read non-zero (exact: nothing but
             # A, N, Z and the cycle counter changes in the loop, and the last iteration runs normally below)
@@ -458,7 +500,11 @@ class Gen:
         self.out.append("#else")
         prev_fell_through = False
         self.open_regions = []
+        self.skip = set()
         for idx, pc in enumerate(order):
+            if pc in self.skip:                   # folded into a closed-form loop
+                prev_fell_through = True
+                continue
             while self.open_regions and self.open_regions[-1] == pc:
                 self.open_regions.pop()
                 self.out.append("  } }  /* end of structured region */")
