@@ -49,6 +49,16 @@ enum {
     NGP_SCHEDULE_ROUND_ROBIN = 1     /* genome i (right) vs genome (i+k) mod N (left), k=1..games */
 };
 
+/* What one entry of the 16-entry gym-retro button vector (8 buttons per player: BUTTON, -, SELECT, RESET, UP, DOWN, LEFT,
+ * RIGHT) does to the console.  Paddle p "up" lowers its resistance.  An environment made with players=1 (the cartridge
+ * robot game, main.py:40) consumes only entries 0..7; FILTERED (main.py:23,55) cancels UP+DOWN / LEFT+RIGHT of one player.
+ * Default map = the reference's own names (config.py:15-20, main.py:91-92): [0] RIGHT_PLAYER_START_BUTTON = fire of paddle 1
+ * (the right player), [15] LEFT_PLAYER_START_BUTTON = fire of paddle 0, [4]/[5] = paddle 1 up/down, [6]/[7] = paddle 0
+ * up/down, [2]/[10] = SELECT, [3]/[11] = RESET.  Which Stella event each retro button really raises is third-party
+ * behaviour that cannot be checked without gym-retro (DESIGN.md "button map"); the map is data so it can be corrected. */
+enum { NGP_BTN_NONE = 0, NGP_BTN_FIRE_P0 = 1 /* +p */, NGP_BTN_UP_P0 = 5 /* +2p = up, +2p+1 = down */, NGP_BTN_SELECT = 13,
+       NGP_BTN_RESET = 14 };
+
 /* Mirror of /root/reference/config.py (names kept) + network shape + schedule. */
 typedef struct {
     int32_t n_layers;                        /* len(NETWORK_SHAPE), config.py:30-32 */
@@ -69,12 +79,15 @@ typedef struct {
     float cxpb, cx_alpha, mutpb, mut_mu, mut_sigma, mut_indpb;
     int32_t tournament_size;                 /* TOURNAMENT_SIZE = POPULATION_SIZE // 4 */
     int32_t core;                            /* 6507 core of the fused rollout: NGP_CORE_* */
+    uint8_t button_map[16];                  /* NGP_BTN_* per gym-retro button (see above) */
 } ngp_config;
 
 typedef struct ngp_handle ngp_handle;
 
 /* Fills cfg with config.py's defaults for a population of `population` genomes. */
 void ngp_default_config(ngp_config *cfg, int32_t population);
+/* sizeof(ngp_config) of the library: a binding asserts its own struct against it before calling ngp_create */
+int32_t ngp_config_size(void);
 const char *ngp_last_error(void);
 const char *ngp_version(void);
 
@@ -145,6 +158,50 @@ int ngp_ga_step(ngp_handle *h, const float *genomes, const double *fitness, int3
                 uint8_t *invalid, double *stats, void *stream);
 /* population init: each gene uniform [0,1) (ga.py:85-87) from Philox(seed) */
 int ngp_init_population(ngp_handle *h, float *genomes, int32_t n, uint64_t seed, void *stream);
+
+/* toolbox.select / toolbox.mate / toolbox.mutate as separate callables (ga.py:89-94), the same arithmetic and the same
+ * Philox streams as ngp_ga_step.
+ * ngp_select: DEAP selTournament(individuals, k, tournsize = cfg.tournament_size): fitness f64[n] -> parent_idx i32[k];
+ *   draws: optional device i32[k][tournsize] aspirant indices (NULL = Philox(seed, generation)).
+ * ngp_mate: DEAP cxBlend(ind1, ind2, cfg.cx_alpha) in place on two device genomes f32[G]; u: optional device f32[G]
+ *   uniforms (NULL = the Philox stream of pair `pair`).
+ * ngp_mutate: DEAP mutGaussian(ind, mu, sigma, indpb) in place; u / z: optional device f32[G] uniforms / standard normals
+ *   (NULL = the Philox streams of individual `slot`). */
+int ngp_select(ngp_handle *h, const double *fitness, int32_t n, int32_t k, const int32_t *draws, uint64_t seed,
+               uint64_t generation, int32_t *parent_idx, void *stream);
+int ngp_mate(ngp_handle *h, float *ind1, float *ind2, const float *u, int32_t pair, uint64_t seed, uint64_t generation,
+             void *stream);
+int ngp_mutate(ngp_handle *h, float *ind, const float *u, const float *z, int32_t slot, uint64_t seed, uint64_t generation,
+               void *stream);
+
+/* ---- hall of fame.  Replaces DEAP tools.HallOfFame(maxsize).update(population) (ga.py:78, main.py:165-168;
+ * consumed by utils.create_model_from_hall_of_fame, utils.py:90-101).  Device resident and caller owned:
+ * hof_genomes f32[maxsize][G] and hof_fitness f64[maxsize] hold the members best first in their first *n_hof rows.
+ * Individuals are visited in population order; one enters when the hall is not full or its fitness is strictly above the
+ * current worst, unless its genes equal a member's (64-bit hash, full compare on a hash match); a full hall drops its worst
+ * first; the newcomer goes BEFORE members of equal fitness (DEAP's bisect_right on the ascending key list).
+ * n_hof (host, in/out): member count.  The call synchronises the stream. */
+int ngp_hof_update(ngp_handle *h, float *hof_genomes, double *hof_fitness, int32_t *n_hof, int32_t maxsize,
+                   const float *genomes, const double *fitness, int32_t n, void *stream);
+
+/* ---- multi-GPU exchange, device side (the reference's toolbox.map = scoop.futures.map gathers every fitness on the
+ * master and eaSimple updates one hall of fame, ga.py:83, main.py:165-170).  One fixed-size record per rank travels in
+ * the per-generation all-gather:
+ *   [ n_local i32 | k_local i32 | 8 B pad | fitness f64[n_max] | elite_fitness f64[k_max] | elite_genomes f32[k_max][G] ]
+ * (ngp_exchange_bytes, a multiple of 16; shards may differ in size when the population does not divide by the world).
+ * ngp_pack_elites writes this rank's record: its n fitness values and its k best individuals, best first (ties: lower
+ * index first).  ngp_unpack_elites reads the gathered records (rank order) and writes the global fitness vector
+ * f64[sum n_r] and the sum k_r elites in rank order, ready to be passed to ngp_hof_update as a population: every rank
+ * then holds the same hall of fame.  Any output may be NULL. */
+int64_t ngp_exchange_bytes(const ngp_handle *h, int32_t n_max, int32_t k_max);
+int ngp_pack_elites(ngp_handle *h, const float *genomes, const double *fitness, int32_t n, int32_t k, int32_t n_max,
+                    int32_t k_max, void *out, void *stream);
+int ngp_unpack_elites(ngp_handle *h, const void *gathered, int32_t world, int32_t n_max, int32_t k_max, double *fitness_all,
+                      float *elite_genomes, double *elite_fitness, void *stream);
+
+/* Tuning switches (experiments, geometry-independence tests): "rollout_block" (threads per CTA), "rollout_nosync",
+ * "rollout_flavour" (1..3), "rollout_blocks_per_sm", "mlp_no_tf32".  value 0 restores the automatic choice. */
+int ngp_set_option(ngp_handle *h, const char *name, int64_t value);
 
 /* Device-side timing of the dominant kernel (the fused rollout) with CUDA events recorded on the
  * launching stream around each launch.  ngp_profile_read synchronises the recorded events, returns

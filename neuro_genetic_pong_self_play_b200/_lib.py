@@ -12,11 +12,15 @@ ACT_NONE, ACT_UP, ACT_DOWN = 0, 1, 2
 STATE_START_1P, STATE_START_2P = 0, 1
 SCHEDULE_REFERENCE, SCHEDULE_ROUND_ROBIN = 0, 1
 CORE_INTERPRETER, CORE_TRANSLATED = 0, 1
+# button map codes (include/ngp.h NGP_BTN_*): fire of paddle p = BTN_FIRE_P0 + p; paddle p up / down = BTN_UP_P0 + 2p / + 2p + 1
+BTN_NONE, BTN_FIRE_P0, BTN_UP_P0, BTN_SELECT, BTN_RESET = 0, 1, 5, 13, 14
 
 EXPORTS = [
     "ngp_default_config", "ngp_last_error", "ngp_version", "ngp_create", "ngp_destroy", "ngp_gene_size",
     "ngp_env_reset", "ngp_env_step", "ngp_env_step_core", "ngp_env_digest", "ngp_find_stuff", "ngp_mlp_forward", "ngp_evaluate",
     "ngp_evaluate_host", "ngp_ga_step", "ngp_init_population", "ngp_launch_count", "ngp_profile_enable", "ngp_profile_read",
+    "ngp_config_size", "ngp_set_option", "ngp_select", "ngp_mate", "ngp_mutate", "ngp_hof_update", "ngp_exchange_bytes",
+    "ngp_pack_elites", "ngp_unpack_elites",
 ]
 
 
@@ -29,6 +33,7 @@ class NgpConfig(ctypes.Structure):
         ("right_colour", ctypes.c_uint8 * 3), ("pad_", ctypes.c_uint8 * 3),
         ("cxpb", ctypes.c_float), ("cx_alpha", ctypes.c_float), ("mutpb", ctypes.c_float), ("mut_mu", ctypes.c_float),
         ("mut_sigma", ctypes.c_float), ("mut_indpb", ctypes.c_float), ("tournament_size", ctypes.c_int32), ("core", ctypes.c_int32),
+        ("button_map", ctypes.c_uint8 * 16),
     ]
 
 
@@ -59,6 +64,9 @@ def load(build_if_missing: bool = True):
         _build.build()
     L = ctypes.CDLL(_build.LIB_PATH)
     vp, i32, u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64
+    L.ngp_config_size.restype = i32
+    if L.ngp_config_size() != ctypes.sizeof(NgpConfig):
+        raise NgpError(f"ngp_config layout mismatch: library {L.ngp_config_size()} bytes, binding {ctypes.sizeof(NgpConfig)}")
     L.ngp_default_config.argtypes = [ctypes.POINTER(NgpConfig), i32]; L.ngp_default_config.restype = None
     L.ngp_last_error.restype = ctypes.c_char_p
     L.ngp_version.restype = ctypes.c_char_p
@@ -78,6 +86,14 @@ def load(build_if_missing: bool = True):
     L.ngp_launch_count.argtypes = [vp]; L.ngp_launch_count.restype = u64
     L.ngp_profile_enable.argtypes = [vp, i32]
     L.ngp_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32)]
+    L.ngp_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
+    L.ngp_select.argtypes = [vp, vp, i32, i32, vp, u64, u64, vp, vp]
+    L.ngp_mate.argtypes = [vp, vp, vp, vp, i32, u64, u64, vp]
+    L.ngp_mutate.argtypes = [vp, vp, vp, vp, i32, u64, u64, vp]
+    L.ngp_hof_update.argtypes = [vp, vp, vp, ctypes.POINTER(i32), i32, vp, vp, i32, vp]
+    L.ngp_exchange_bytes.argtypes = [vp, i32, i32]; L.ngp_exchange_bytes.restype = ctypes.c_int64
+    L.ngp_pack_elites.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    L.ngp_unpack_elites.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -43,6 +43,10 @@ class Config:
     SCHEDULE: int = _lib.SCHEDULE_REFERENCE
     MAX_FRAMES: int = 0
     CORE: int = _lib.CORE_TRANSLATED           # 6507 core of the fused rollout
+    # what each gym-retro button does to the console (include/ngp.h NGP_BTN_*); default = the reference's own names:
+    # [0] RIGHT_PLAYER_START_BUTTON -> fire of paddle 1, [15] LEFT_PLAYER_START_BUTTON -> fire of paddle 0,
+    # [4]/[5] right player (paddle 1) up/down, [6]/[7] left player (paddle 0) up/down, SELECT / RESET of either player
+    BUTTON_MAP: Tuple[int, ...] = (2, 0, 13, 14, 7, 8, 5, 6, 0, 0, 13, 14, 0, 0, 0, 1)
 
     @property
     def GAME_PLAYABLE_HEIGHT(self) -> int:
@@ -95,4 +99,7 @@ class Config:
         c.mut_indpb = self.PROBABILITY_OF_MUTATING_A_SINGLE_GENE
         c.tournament_size = self.TOURNAMENT_SIZE
         c.core = self.CORE
+        assert len(self.BUTTON_MAP) == 16
+        for i, code in enumerate(self.BUTTON_MAP):
+            c.button_map[i] = code
         return c

@@ -10,6 +10,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "ngp_internal.h"
@@ -63,6 +65,13 @@ extern "C" void ngp_default_config(ngp_config *cfg, int32_t population)
     cfg->cxpb = 0.9f; cfg->cx_alpha = 0.9f; cfg->mutpb = 0.9f; cfg->mut_mu = 0.0f; cfg->mut_sigma = 0.9f; cfg->mut_indpb = 0.9f;
     cfg->tournament_size = population / 4;
     cfg->core = NGP_CORE_TRANSLATED;
+    // button map: the reference's own naming (config.py:15-20, main.py:91-92) -- see include/ngp.h
+    cfg->button_map[0] = NGP_BTN_FIRE_P0 + 1;      // RIGHT_PLAYER_START_BUTTON = 0
+    cfg->button_map[15] = NGP_BTN_FIRE_P0 + 0;     // LEFT_PLAYER_START_BUTTON = -1
+    cfg->button_map[4] = NGP_BTN_UP_P0 + 2; cfg->button_map[5] = NGP_BTN_UP_P0 + 3;      // action[4:6]: right player = paddle 1
+    cfg->button_map[6] = NGP_BTN_UP_P0 + 0; cfg->button_map[7] = NGP_BTN_UP_P0 + 1;      // action[6:8]: left player = paddle 0
+    cfg->button_map[2] = cfg->button_map[10] = NGP_BTN_SELECT;
+    cfg->button_map[3] = cfg->button_map[11] = NGP_BTN_RESET;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -70,6 +79,7 @@ extern "C" void ngp_default_config(ngp_config *cfg, int32_t population)
 // ------------------------------------------------------------------------------------------------
 using a26::Chip; using a26::CpuRegs; using a26::Ram; using a26::Snapshot; using a26::Tables;
 using roll::RolloutParams; using roll::load_snapshot; using roll::store_snapshot; using roll::action_to_input;
+using pol::ACT_UP; using pol::ACT_DOWN;
 
 __device__ __forceinline__ void load_tables(Tables &dst, const Tables *__restrict__ src)
 {
@@ -104,8 +114,10 @@ __global__ void env_reset_kernel(const Snapshot *start, Snapshot *envs, int n)
     if (i < n) envs[i] = *start;
 }
 
+struct ButtonMap { uint8_t m[16]; };
+
 template <bool VERIFY>
-__global__ void __launch_bounds__(32) env_step_kernel(const Tables *tables, const uint32_t *needed, Snapshot *envs, int n, int core,
+__global__ void __launch_bounds__(32) env_step_kernel(const Tables *tables, const uint32_t *needed, Snapshot *envs, int n, int core, int players, ButtonMap map,
                                                       const uint8_t *actions, uint8_t *fb, uint8_t *ram_out, float *loc,
                                                       uint8_t *valid, uint8_t *regs, unsigned long long *counters)
 {
@@ -117,9 +129,8 @@ __global__ void __launch_bounds__(32) env_step_kernel(const Tables *tables, cons
     Ram ram{&ram_smem[threadIdx.x]};
     Chip s; CpuRegs r;
     load_snapshot(&envs[e], s, r, ram);
-    uint32_t fire, dec, inc;
-    action_to_input(actions + (size_t)e * 16, fire, dec, inc);
-    a26::apply_input(s, needed, 0x3F, fire, dec, inc);
+    const uint32_t in = action_to_input(actions + (size_t)e * 16, players, map.m);
+    a26::apply_input(s, needed, in & 0xFF, (in >> 8) & 15, (in >> 12) & 15, (in >> 16) & 15);
     a26::clear_obs(s);
     uint8_t *my_fb = fb ? fb + (size_t)e * a26::FB_ROWS * a26::FB_COLS : nullptr;
     if (core) a26::run_frame_compiled<VERIFY, false>(s, r, T, ram, my_fb);
@@ -231,6 +242,31 @@ static int gene_size_of(const ngp_config &c)
 extern "C" int32_t ngp_gene_size(const ngp_handle *h) { return h ? h->gene_size : 0; }
 extern "C" uint64_t ngp_launch_count(const ngp_handle *h) { return h ? h->launches : 0; }
 
+static std::mutex g_start_mutex;
+static std::map<uint64_t, std::vector<Snapshot>> g_start_cache;       // cartridge hash -> {'Start', 'Start.2P'} (immutable)
+static uint64_t fnv1a64(const uint8_t *p, size_t n)
+{
+    uint64_t hsh = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { hsh ^= p[i]; hsh *= 1099511628211ull; }
+    return hsh;
+}
+
+extern "C" int32_t ngp_config_size(void) { return (int32_t)sizeof(ngp_config); }
+
+// Tuning switches that used to be environment variables; 0 restores the automatic choice.
+extern "C" int ngp_set_option(ngp_handle *h, const char *name, int64_t value)
+{
+    NGP_REQUIRE(h && name, "ngp_set_option: bad arguments");
+    const std::string n(name);
+    if (n == "rollout_block") h->opt_rollout_block = (int)value;
+    else if (n == "rollout_nosync") h->opt_rollout_nosync = value != 0;
+    else if (n == "rollout_flavour") h->opt_rollout_lean = (int)value;
+    else if (n == "rollout_blocks_per_sm") h->opt_rollout_blocks_per_sm = (int)value;
+    else if (n == "mlp_no_tf32") h->opt_mlp_no_tf32 = value != 0;
+    else { ngp_set_error("ngp_set_option: unknown option '%s'", name); return NGP_ERR_INVALID; }
+    return NGP_OK;
+}
+
 extern "C" int ngp_create(const ngp_config *cfg, const uint8_t *rom, int32_t device, ngp_handle **out)
 {
     NGP_REQUIRE(cfg && rom && out, "ngp_create: null argument");
@@ -266,9 +302,23 @@ extern "C" int ngp_create(const ngp_config *cfg, const uint8_t *rom, int32_t dev
     NGP_CUDA(cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)));
     NGP_CUDA(cudaMemset(h->d_counters, 0, 4 * sizeof(unsigned long long)));
     NGP_CUDA(cudaMallocHost(&h->h_counters, 4 * sizeof(unsigned long long)));
-    build_start_states_kernel<<<1, 32>>>(h->d_tables, h->d_needed, h->d_start);
-    h->launches++;
-    NGP_CUDA(cudaGetLastError());
+    // The two start snapshots depend on the cartridge image only: built once per process by the CUDA core (a single warp,
+    // tens of milliseconds) and kept as an immutable host copy for later handles.
+    {
+        std::lock_guard<std::mutex> lock(g_start_mutex);
+        const uint64_t key = fnv1a64(rom, 2048);
+        auto it = g_start_cache.find(key);
+        if (it == g_start_cache.end()) {
+            build_start_states_kernel<<<1, 32>>>(h->d_tables, h->d_needed, h->d_start);
+            h->launches++;
+            NGP_CUDA(cudaGetLastError());
+            std::vector<Snapshot> snap(2);
+            NGP_CUDA(cudaMemcpy(snap.data(), h->d_start, 2 * sizeof(Snapshot), cudaMemcpyDeviceToHost));
+            g_start_cache.emplace(key, std::move(snap));
+        } else {
+            NGP_CUDA(cudaMemcpy(h->d_start, it->second.data(), 2 * sizeof(Snapshot), cudaMemcpyHostToDevice));
+        }
+    }
     NGP_CUDA(cudaDeviceSynchronize());
     *out = h;
     return NGP_OK;
@@ -281,6 +331,8 @@ extern "C" int ngp_destroy(ngp_handle *h)
     cudaFree(h->d_tables); cudaFree(h->d_needed); cudaFree(h->d_palette); cudaFree(h->d_start);
     cudaFree(h->d_envs); cudaFree(h->d_fb); cudaFree(h->d_rewards); cudaFree(h->d_frames); cudaFree(h->d_counters);
     cudaFree(h->d_genomes_stage); cudaFree(h->d_fitness_stage); cudaFree(h->d_hof_stage); cudaFree(h->d_hof_fit_stage);
+    cudaFree(h->mlp_a); cudaFree(h->mlp_b); cudaFree(h->mlp_z); cudaFree(h->d_parent);
+    cudaFree(h->hof_hash_old); cudaFree(h->hof_hash_new); cudaFree(h->hof_order); cudaFree(h->hof_tmp_genomes); cudaFree(h->hof_tmp_fitness);
     cudaFreeHost(h->h_genomes); cudaFreeHost(h->h_fitness); cudaFreeHost(h->h_counters);
     if (h->prof_events) { for (auto &e : *h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } delete h->prof_events; }
     delete h;
@@ -301,6 +353,7 @@ extern "C" int ngp_env_reset(ngp_handle *h, int32_t n_envs, int32_t state_id, vo
         h->cap_envs = n_envs;
     }
     h->n_envs = n_envs;
+    h->env_players = state_id == NGP_STATE_START_1P ? 1 : 2;     // main.py:40 makes the robot game with players=1
     env_reset_kernel<<<(n_envs + 127) / 128, 128, 0, st>>>(h->d_start + state_id, h->d_envs, n_envs);
     h->launches++;
     NGP_CUDA(cudaGetLastError());
@@ -327,13 +380,15 @@ extern "C" int ngp_env_step_core(ngp_handle *h, int32_t core, const uint8_t *act
     cudaStream_t st = (cudaStream_t)stream;
     const int n = h->n_envs;
     const size_t px = (size_t)n * a26::FB_ROWS * a26::FB_COLS;
+    ButtonMap bmap;
+    memcpy(bmap.m, h->cfg.button_map, 16);
     if (frames) NGP_CUDA(cudaMemsetAsync(h->d_fb, 0, px, st));
     // with a frame requested every pixel is rendered (verify mode); without, the fused no-framebuffer flavour runs
     if (frames)
-        env_step_kernel<true><<<(n + 31) / 32, 32, 0, st>>>(h->d_tables, h->d_needed, h->d_envs, n, core ? 1 : 0, actions, h->d_fb, ram,
+        env_step_kernel<true><<<(n + 31) / 32, 32, 0, st>>>(h->d_tables, h->d_needed, h->d_envs, n, core ? 1 : 0, h->env_players, bmap, actions, h->d_fb, ram,
                                                             loc, valid, regs, h->d_counters);
     else
-        env_step_kernel<false><<<(n + 31) / 32, 32, 0, st>>>(h->d_tables, h->d_needed, h->d_envs, n, core ? 1 : 0, actions, nullptr, ram,
+        env_step_kernel<false><<<(n + 31) / 32, 32, 0, st>>>(h->d_tables, h->d_needed, h->d_envs, n, core ? 1 : 0, h->env_players, bmap, actions, nullptr, ram,
                                                              loc, valid, regs, h->d_counters);
     h->launches++;
     NGP_CUDA(cudaGetLastError());
@@ -394,6 +449,15 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
     p.win_score = h->cfg.win_score; p.timeout_thresh = h->cfg.timeout_thresh; p.max_frames = h->cfg.max_frames;
     p.time_scaler = (double)h->cfg.time_scaler; p.paddle_height = (double)h->cfg.scaled_paddle_height;
     p.seed = seed; p.generation = generation; p.shape = h->shape;
+    for (int players = 1; players <= 2; ++players)
+        for (int la = 0; la < 3; ++la)
+            for (int ra = 0; ra < 3; ++ra) {
+                uint8_t a[16] = {0};
+                a[0] = 1; a[15] = 1;                                          // BLANK_ACTION, config.py:21-23
+                a[4] = ra == pol::ACT_UP; a[5] = ra == pol::ACT_DOWN;         // action[4:6] = right (main.py:91)
+                a[6] = la == pol::ACT_UP; a[7] = la == pol::ACT_DOWN;         // action[6:8] = left (main.py:92)
+                p.input_table[players - 1][la * 3 + ra] = roll::action_to_input(a, players, h->cfg.button_map);
+            }
     p.rewards = rewards ? rewards : h->d_rewards; p.frames = frames ? frames : h->d_frames; p.counters = h->d_counters;
     // Launch geometry (measured, profiles/README.md).  Small launches: one-warp CTAs spread over all SMs.  From ~2 warps per
     // SM upwards the CTA-synchronous flavour wins: all warps of a CTA walk through the frame together and share their
@@ -408,27 +472,29 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
         else if (total <= (long long)h->sm_count * 384) block = 384;
         else block = 512;
     } else if (!p.core && warps > (long long)h->sm_count * 16) block = 128;
-    // tuning overrides (experiments only)
-    if (const char *e = getenv("NGP_ROLLOUT_BLOCK")) { int b = atoi(e); if (b >= 32 && b <= 1024 && b % 32 == 0) block = b; }
-    const bool sync = p.core && block > 32 && !getenv("NGP_ROLLOUT_NOSYNC");
+    // tuning overrides (ngp_set_option; experiments and the geometry-independence tests only)
+    if (h->opt_rollout_block >= 32 && h->opt_rollout_block <= 1024 && h->opt_rollout_block % 32 == 0) block = h->opt_rollout_block;
+    const bool sync = p.core && block > 32 && !h->opt_rollout_nosync;
     // register budget: MAXT=256 lets the compiler have the ~210-230 registers it wants (no spills: +8 % per one-warp CTA, +22 %
-    // for CTA-synchronous launches, measured); MAXT=384 gives 168, MAXT=512 caps them at 128 (16 warps per SM), MAXT=640 at 96.
+    // for CTA-synchronous launches, measured); MAXT=384 gives 168, MAXT=512 caps them at 128 (16 warps per SM).
     // While every CTA has an SM to itself the fattest flavour that fits the CTA is used; beyond that occupancy is worth more
     // than the spills.
     long long blocks = (total + block - 1) / block;
     const bool one_per_sm = blocks <= (long long)h->sm_count;
-    int lean = sync ? (one_per_sm && block <= 256 ? 0 : one_per_sm && block <= 384 ? 3 : 1) : 0;
-    if (const char *e = getenv("NGP_ROLLOUT_LEAN")) lean = atoi(e);
+    int lean = sync ? (one_per_sm && block <= 256 ? 0 : one_per_sm && block <= 384 ? 2 : 1) : 0;
+    if (h->opt_rollout_lean) lean = h->opt_rollout_lean - 1;       // option value 1..3 = flavour 0 (256), 1 (512), 2 (384)
     if (!sync) lean = 0;
+    if (sync && block > (lean == 0 ? 256 : lean == 2 ? 384 : 512)) lean = block > 384 ? 1 : 2;   // the flavour's launch bound must hold the CTA
+    NGP_REQUIRE(block <= (sync ? 512 : p.core ? 256 : 384), "ngp_evaluate: rollout_block exceeds the kernel flavour's launch bound");
     auto kernel = !p.core ? rollout_kernel<0, false, 384>
                           : (!sync ? rollout_kernel<1, false, 256>
-                                   : (lean == 3 ? rollout_kernel<1, true, 384> : lean == 2 ? rollout_kernel<1, true, 640> : lean == 1 ? rollout_kernel<1, true, 512> : rollout_kernel<1, true, 256>));
+                                   : (lean == 2 ? rollout_kernel<1, true, 384> : lean == 1 ? rollout_kernel<1, true, 512> : rollout_kernel<1, true, 256>));
     const size_t smem = (size_t)block * 32 * 4;
     int per_sm = 0;
     if (smem + sizeof(Tables) > 48 * 1024) NGP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
     if (per_sm < 1) per_sm = 1;
-    if (const char *e = getenv("NGP_ROLLOUT_BLOCKS_PER_SM")) { int b = atoi(e); if (b >= 1 && b < per_sm) per_sm = b; }
+    if (h->opt_rollout_blocks_per_sm >= 1 && h->opt_rollout_blocks_per_sm < per_sm) per_sm = h->opt_rollout_blocks_per_sm;
     const long long resident = (long long)per_sm * h->sm_count;
     if (blocks > resident) blocks = resident;            // persistent lanes pull the rest from the queue
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

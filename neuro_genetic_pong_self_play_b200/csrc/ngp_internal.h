@@ -27,6 +27,7 @@ struct ngp_handle {
     a26::Snapshot *d_envs;
     uint8_t *d_fb;                // palette-index frames [n_envs][210][160]
     int n_envs, cap_envs;
+    int env_players;              // gym-retro `players` of the state the stepwise environments were reset to (1 for 'Start')
     // fused evaluation scratch
     double *d_rewards;            // [cap_eval]
     int32_t *d_frames;            // [cap_eval]
@@ -38,6 +39,15 @@ struct ngp_handle {
     float *d_hof_stage; double *d_hof_fit_stage; size_t stage_hof;
     unsigned long long *h_counters;
     uint64_t launches;
+    // per-handle scratch of the operator entry points (nothing here is shared between handles)
+    float *mlp_a, *mlp_b; double *mlp_z; size_t mlp_cap_ab, mlp_cap_z;      // ngp_mlp_forward activations
+    int32_t *d_parent; size_t cap_parent;                                   // ngp_ga_step selection winners
+    uint64_t *hof_hash_old, *hof_hash_new; int32_t *hof_order; float *hof_tmp_genomes; double *hof_tmp_fitness;   // ngp_hof_update
+    size_t hof_cap_hash_old, hof_cap_hash_new, hof_cap_order, hof_cap_tmp_genomes, hof_cap_tmp_fitness;
+    int fs_per_sm;                                                          // resident find_stuff CTAs per SM
+    int tf32_attr_set;                                                      // dynamic shared memory opt-in done
+    // ngp_set_option (tuning experiments; 0 = automatic)
+    int opt_rollout_block, opt_rollout_nosync, opt_rollout_lean, opt_rollout_blocks_per_sm, opt_mlp_no_tf32;
     // profiling of the rollout kernel
     int profile_on;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *prof_events;

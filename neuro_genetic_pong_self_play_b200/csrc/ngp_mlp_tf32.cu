@@ -275,10 +275,9 @@ int ngp_mlp_layer_tf32(ngp_handle *h, const float *genomes, size_t w_off, const 
                        float *out, cudaStream_t st)
 {
     if (ni < 64 || no < 64 || envs < 16) return NGP_ERR_UNSUPPORTED;
-    static bool attr_set[64];
-    if (!attr_set[h->device]) {
+    if (!h->tf32_attr_set) {
         NGP_CUDA(cudaFuncSetAttribute(tf32::v2::mlp_layer_tf32_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf32::v2::SMEM2));
-        attr_set[h->device] = true;
+        h->tf32_attr_set = 1;
     }
     dim3 grid((no + tf32::TM - 1) / tf32::TM, (envs + tf32::TN - 1) / tf32::TN, n_genomes);
     tf32::v2::mlp_layer_tf32_v2_kernel<<<grid, tf32::v2::THREADS2, tf32::v2::SMEM2, st>>>(genomes, w_off, h->gene_size, in, envs, ni, no, bias, out);

@@ -151,11 +151,12 @@ extern "C" int ngp_find_stuff(ngp_handle *h, const uint8_t *frames, int32_t n, f
                 pat.w[phase][t][w] = v;
             }
     // persistent CTAs over frames, as many as are resident at once
-    static int per_sm = 0;
-    if (!per_sm) {
-        NGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, find_stuff_kernel, FS_THREADS, 0));
-        if (per_sm < 1) per_sm = 1;
+    if (!h->fs_per_sm) {
+        int per = 0;
+        NGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, find_stuff_kernel, FS_THREADS, 0));
+        h->fs_per_sm = per < 1 ? 1 : per;
     }
+    const int per_sm = h->fs_per_sm;
     int grid = n < h->sm_count * per_sm ? n : h->sm_count * per_sm;
     find_stuff_kernel<<<grid, FS_THREADS, 0, (cudaStream_t)stream>>>(frames, n, pat, loc, valid);
     h->launches++;
@@ -445,8 +446,7 @@ __global__ void mlp_decide_kernel(const double *__restrict__ z, long long rows, 
 int ngp_mlp_layer_tf32(ngp_handle *h, const float *genomes, size_t w_off, const float *in, int n_genomes, int envs, int ni, int no, int bias,
                        float *out, cudaStream_t st);   // ngp_mlp_tf32.cu
 
-struct MlpScratch { float *a, *b; double *z; size_t cap_ab, cap_z; };
-static MlpScratch g_mlp_scratch[64];   // per device
+struct MlpScratch { float *&a, *&b; double *&z; size_t &cap_ab, &cap_z; };     // view of the handle's scratch
 
 extern "C" int ngp_mlp_forward(ngp_handle *h, const float *genomes, const float *x, int32_t n_genomes, int32_t envs, uint8_t *act,
                                float *out, void *stream)
@@ -464,7 +464,7 @@ extern "C" int ngp_mlp_forward(ngp_handle *h, const float *genomes, const float 
         NGP_CUDA(cudaGetLastError());
         return NGP_OK;
     }
-    MlpScratch &sc = g_mlp_scratch[h->device];
+    MlpScratch sc{h->mlp_a, h->mlp_b, h->mlp_z, h->mlp_cap_ab, h->mlp_cap_z};
     const size_t need_ab = (size_t)rows * widest, need_z = (size_t)rows * sh.nodes[sh.n_layers - 1];
     if (need_ab > sc.cap_ab) {
         cudaFree(sc.a); cudaFree(sc.b); sc.cap_ab = 0;
@@ -508,7 +508,7 @@ extern "C" int ngp_mlp_forward(ngp_handle *h, const float *genomes, const float 
             NGP_CUDA(cudaGetLastError());
             launched = true;
         }
-        if (!launched && l != L - 1 && !getenv("NGP_MLP_NO_TF32")) {
+        if (!launched && l != L - 1 && !h->opt_mlp_no_tf32) {
             // wide hidden layer with enough environments per genome: tensor cores (3xTF32, tcgen05 + TMEM)
             const int rc = ngp_mlp_layer_tf32(h, genomes, w_off, in, n_genomes, envs, ni, no, bias, bufs[l & 1], st);
             if (rc == NGP_OK) launched = true;
@@ -533,10 +533,7 @@ extern "C" int ngp_mlp_forward(ngp_handle *h, const float *genomes, const float 
 // K4: GA step.  Counter-based RNG: Philox4x32-10 keyed by the seed; the counter encodes
 // (slot, block-within-slot, generation, stream) so results do not depend on launch geometry.
 // =================================================================================================
-enum : uint32_t { STREAM_SELECT = 0x53454C31u, STREAM_CXDO = 0x43584431u, STREAM_CXU = 0x43585531u, STREAM_MUTDO = 0x4D544431u,
-                  STREAM_MUTU = 0x4D545531u, STREAM_MUTZ = 0x4D545A31u, STREAM_INIT = 0x494E4931u };
-
-__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }   // [0,1)
+#include "ga_streams.cuh"
 
 __global__ void init_population_kernel(float *__restrict__ genomes, long long total, uint64_t seed)
 {
@@ -585,12 +582,12 @@ __global__ void __launch_bounds__(1024) fitness_stats_kernel(const double *__res
 
 // selTournament: one warp per offspring slot; lanes split the T draws; winner = max fitness, first in
 // draw order on ties.
-__global__ void __launch_bounds__(256) select_tournament_kernel(const double *__restrict__ fitness, int n, int T, const int32_t *__restrict__ draws,
+__global__ void __launch_bounds__(256) select_tournament_kernel(const double *__restrict__ fitness, int n, int k, int T, const int32_t *__restrict__ draws,
                                                                 uint64_t seed, uint64_t generation, int32_t *__restrict__ parent_idx)
 {
     const int slot = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (slot >= n) return;
+    if (slot >= k) return;
     double best_f = -INFINITY;
     int best_pos = 0x7FFFFFFF, best_idx = -1;
     if (draws) {
@@ -647,11 +644,7 @@ __global__ void __launch_bounds__(256) vary_kernel(const float *__restrict__ gen
         float u;
         if (noise.cx_u) u = noise.cx_u[(size_t)pair * G + gene];
         else { pol::philox4x32((uint32_t)pair, (uint32_t)(gene >> 2), gen, STREAM_CXU, k0, k1, o); u = u01(o[gene & 3]); }
-        const float gamma = __fsub_rn(__fmul_rn((float)(1.0 + 2.0 * (double)alpha), u), alpha);
-        const float one_m = __fsub_rn(1.0f, gamma);
-        const float c0 = __fadd_rn(__fmul_rn(one_m, x0), __fmul_rn(gamma, x1));
-        const float c1 = __fadd_rn(__fmul_rn(gamma, x0), __fmul_rn(one_m, x1));
-        x0 = c0; x1 = c1;
+        blend_gene(alpha, u, x0, x1);
     }
     // ---- mutate (ga.py:91-92, mutGaussian) ----
     bool do_mut[2];
@@ -665,12 +658,7 @@ __global__ void __launch_bounds__(256) vary_kernel(const float *__restrict__ gen
             if (noise.mut_u) u = noise.mut_u[(size_t)ind * G + gene];
             else { pol::philox4x32((uint32_t)ind, (uint32_t)(gene >> 2), gen, STREAM_MUTU, k0, k1, o); u = u01(o[gene & 3]); }
             if (noise.mut_z) z = noise.mut_z[(size_t)ind * G + gene];
-            else {      // Box-Muller on two words of a per-gene Philox block
-                pol::philox4x32((uint32_t)ind, (uint32_t)gene, gen, STREAM_MUTZ, k0, k1, o);
-                const float u1 = ((float)(o[0] >> 8) + 1.0f) * (1.0f / 16777216.0f);      // (0,1]
-                const float u2 = u01(o[1]);
-                z = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
-            }
+            else z = mut_normal((uint32_t)ind, (uint32_t)gene, gen, k0, k1);
             if (u < indpb) {
                 const float step = __fadd_rn(mu, __fmul_rn(sigma, z));
                 if (s) x1 = __fadd_rn(x1, step); else x0 = __fadd_rn(x0, step);
@@ -685,9 +673,6 @@ __global__ void __launch_bounds__(256) vary_kernel(const float *__restrict__ gen
     }
 }
 
-static int32_t *g_parent_scratch[64];
-static size_t g_parent_cap[64];
-
 extern "C" int ngp_ga_step(ngp_handle *h, const float *genomes, const double *fitness, int32_t n, uint64_t seed, uint64_t generation,
                            const ngp_noise *noise, float *next, int32_t *parent_idx, uint8_t *invalid, double *stats, void *stream)
 {
@@ -701,25 +686,39 @@ extern "C" int ngp_ga_step(ngp_handle *h, const float *genomes, const double *fi
     int T = h->cfg.tournament_size;
     if (T < 1) T = 1;
     if (!parent_idx) {
-        if ((size_t)n > g_parent_cap[h->device]) {
-            cudaFree(g_parent_scratch[h->device]); g_parent_cap[h->device] = 0;
-            NGP_CUDA(cudaMalloc(&g_parent_scratch[h->device], (size_t)n * sizeof(int32_t)));
-            g_parent_cap[h->device] = n;
+        if ((size_t)n > h->cap_parent) {
+            cudaFree(h->d_parent); h->d_parent = nullptr; h->cap_parent = 0;
+            NGP_CUDA(cudaMalloc(&h->d_parent, (size_t)n * sizeof(int32_t)));
+            h->cap_parent = n;
         }
-        parent_idx = g_parent_scratch[h->device];
+        parent_idx = h->d_parent;
     }
     if (stats) {
         fitness_stats_kernel<<<1, 1024, 0, st>>>(fitness, n, stats);
         h->launches++;
         NGP_CUDA(cudaGetLastError());
     }
-    select_tournament_kernel<<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(fitness, n, T, nz.sel_draws, seed, generation, parent_idx);
+    select_tournament_kernel<<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(fitness, n, n, T, nz.sel_draws, seed, generation, parent_idx);
     h->launches++;
     NGP_CUDA(cudaGetLastError());
     const long long work = (long long)((n + 1) / 2) * h->gene_size;
     vary_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(genomes, parent_idx, n, h->gene_size, nz, seed, generation, h->cfg.cxpb,
                                                                h->cfg.cx_alpha, h->cfg.mutpb, h->cfg.mut_mu, h->cfg.mut_sigma,
                                                                h->cfg.mut_indpb, next, invalid);
+    h->launches++;
+    NGP_CUDA(cudaGetLastError());
+    return NGP_OK;
+}
+
+extern "C" int ngp_select(ngp_handle *h, const double *fitness, int32_t n, int32_t k, const int32_t *draws, uint64_t seed,
+                          uint64_t generation, int32_t *parent_idx, void *stream)
+{
+    NGP_REQUIRE(h && fitness && parent_idx && n > 0 && k > 0, "ngp_select: bad arguments");
+    NGP_CUDA(cudaSetDevice(h->device));
+    int T = h->cfg.tournament_size;
+    if (T < 1) T = 1;
+    select_tournament_kernel<<<(unsigned)(((long long)k * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fitness, n, k, T, draws, seed, generation,
+                                                                                                     parent_idx);
     h->launches++;
     NGP_CUDA(cudaGetLastError());
     return NGP_OK;

@@ -35,11 +35,11 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// the per-frame random action bit of get_actions (main.py:139-140)
-__device__ __forceinline__ uint32_t random_action_bit(uint64_t seed, uint32_t env_id, uint32_t frame, uint32_t stream)
+// the per-frame random action bit of get_actions (main.py:139-140): fresh for every (generation, environment, frame, player)
+__device__ __forceinline__ uint32_t random_action_bit(uint64_t seed, uint64_t generation, uint32_t env_id, uint32_t frame, uint32_t stream)
 {
     uint32_t o[4];
-    philox4x32(env_id, frame, stream, 0x504F4E47u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    philox4x32(env_id, frame, ((uint32_t)generation << 1) | stream, 0x504F4E47u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
     return o[0] & 1u;
 }
 

@@ -29,13 +29,25 @@ __device__ __forceinline__ void store_snapshot(Snapshot *dst, const Chip &s, con
     for (int i = 0; i < 32; ++i) w[i] = ram.base[i * 32];
 }
 
-// gym-retro button vector -> console input (config.py:15-23, main.py:91-92; DESIGN.md "button map")
-__device__ __forceinline__ void action_to_input(const uint8_t *a, uint32_t &fire, uint32_t &dec, uint32_t &inc)
+// gym-retro button vector -> console input through the configurable button map (ngp_config.button_map; include/ngp.h
+// NGP_BTN_*; DESIGN.md "button map").  An environment made with players=1 (main.py:40) consumes only a[0:8].
+// FILTERED (main.py:23,55): UP+DOWN or LEFT+RIGHT of one player cancel.  Returns swchb | fire << 8 | dec << 12 | inc << 16.
+__host__ __device__ __forceinline__ uint32_t action_to_input(const uint8_t *a, int players, const uint8_t *map)
 {
-    fire = (a[15] ? 1u : 0u) | (a[0] ? 2u : 0u);
-    dec = inc = 0;
-    if ((a[4] != 0) != (a[5] != 0)) { if (a[4]) dec |= 2; else inc |= 2; }   // right paddle = paddle 1
-    if ((a[6] != 0) != (a[7] != 0)) { if (a[6]) dec |= 1; else inc |= 1; }   // left paddle  = paddle 0
+    uint32_t swchb = 0x3F, fire = 0, dec = 0, inc = 0;
+    for (int i = 0; i < 8 * players; ++i) {
+        if (!a[i]) continue;
+        const int j = i & 7;
+        if (j >= 4 && a[i ^ 1]) continue;            // opposite direction held too (pairs 4/5 and 6/7)
+        const int code = map[i];
+        if (code >= NGP_BTN_FIRE_P0 && code <= NGP_BTN_FIRE_P0 + 3) fire |= 1u << (code - NGP_BTN_FIRE_P0);
+        else if (code >= NGP_BTN_UP_P0 && code < NGP_BTN_UP_P0 + 8) {
+            const int k = code - NGP_BTN_UP_P0;
+            if (k & 1) inc |= 1u << (k >> 1); else dec |= 1u << (k >> 1);      // up = lower resistance
+        } else if (code == NGP_BTN_SELECT) swchb &= ~0x02u;
+        else if (code == NGP_BTN_RESET) swchb &= ~0x01u;
+    }
+    return swchb | (fire << 8) | (dec << 12) | (inc << 16);
 }
 
 // power-on + scripted console switches up to the reference's save states (DESIGN.md "start states")
@@ -55,13 +67,6 @@ __device__ __forceinline__ void build_start_state(int state, Chip &s, CpuRegs &r
     idle(0x3F, 1);                                   // gym-retro reset(): one frame without buttons
 }
 
-__device__ __forceinline__ void acts_to_input(int left_act, int right_act, uint32_t &fire, uint32_t &dec, uint32_t &inc)
-{
-    fire = 3;      // BLANK_ACTION holds both start buttons (config.py:21-23)
-    dec = (left_act == pol::ACT_UP ? 1u : 0u) | (right_act == pol::ACT_UP ? 2u : 0u);
-    inc = (left_act == pol::ACT_DOWN ? 1u : 0u) | (right_act == pol::ACT_DOWN ? 2u : 0u);
-}
-
 struct RolloutParams {
     const Tables *tables;
     const uint32_t *needed;
@@ -72,6 +77,9 @@ struct RolloutParams {
     const int32_t *hof_pick;        // [n][3] or null
     int n, n_hof, G, games, schedule, win_score, timeout_thresh, max_frames;
     int core;                       // 0 = table-driven interpreter, 1 = statically translated cartridge
+    // console input of perform_episode's action vector (BLANK_ACTION with the two decisions written to a[4:6] / a[6:8],
+    // config.py:21-23, main.py:91-92) for players = 1, 2 and every (left_act, right_act): action_to_input() done on the host
+    uint32_t input_table[2][9];
     double time_scaler, paddle_height;
     uint64_t seed, generation;
     pol::Shape shape;
@@ -160,9 +168,8 @@ __device__ __forceinline__ bool episode_frame(Episode &ep, const RolloutParams &
                                               double *reward, bool active = true)
 {
     if (active) {
-        uint32_t fire, dec, inc;
-        acts_to_input(ep.left_act, ep.right_act, fire, dec, inc);
-        a26::apply_input(s, p.needed, 0x3F, fire, dec, inc);
+        const uint32_t in = p.input_table[ep.plan.state == NGP_STATE_START_1P ? 0 : 1][ep.left_act * 3 + ep.right_act];
+        a26::apply_input(s, p.needed, in & 0xFF, (in >> 8) & 15, (in >> 12) & 15, (in >> 16) & 15);
         a26::clear_obs(s);
     }
     if (CORE) a26::run_frame_compiled<false, SYNC>(s, r, T, ram, nullptr, active);
@@ -190,8 +197,8 @@ __device__ __forceinline__ bool episode_frame(Episode &ep, const RolloutParams &
             left_act = run_policy(p.shape, ep.plan.left_kind, ep.plan.left_genome, fball, flast, loc[1][0], loc[2][0], s1, s2);
             right_act = run_policy(p.shape, pol::KIND_MLP, ep.plan.right_genome, loc[0], lb, loc[2][0], loc[1][0], s1, s2);
         } else {
-            left_act = pol::random_action_bit(p.seed, (uint32_t)ep.env, (uint32_t)ep.frame, 0) ? pol::ACT_DOWN : pol::ACT_UP;
-            right_act = pol::random_action_bit(p.seed, (uint32_t)ep.env, (uint32_t)ep.frame, 1) ? pol::ACT_DOWN : pol::ACT_UP;
+            left_act = pol::random_action_bit(p.seed, p.generation, (uint32_t)ep.env, (uint32_t)ep.frame, 0) ? pol::ACT_DOWN : pol::ACT_UP;
+            right_act = pol::random_action_bit(p.seed, p.generation, (uint32_t)ep.env, (uint32_t)ep.frame, 1) ? pol::ACT_DOWN : pol::ACT_UP;
         }
     }
     ep.have_last_ball = valid[0];

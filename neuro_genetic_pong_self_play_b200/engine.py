@@ -76,6 +76,10 @@ class Engine:
         _lib.check(self._L.ngp_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n)), "ngp_profile_read")
         return ms.value, n.value
 
+    def set_option(self, name: str, value: int):
+        """Tuning switch (include/ngp.h: ngp_set_option); 0 restores the automatic choice."""
+        _lib.check(self._L.ngp_set_option(self._h, name.encode(), int(value)), "ngp_set_option")
+
     def _check_tensor(self, t: torch.Tensor, dtype, name: str):
         if not (t.is_cuda and t.device == self.device and t.dtype == dtype and t.is_contiguous()):
             raise ValueError(f"{name}: expected a contiguous {dtype} tensor on {self.device}")
@@ -190,3 +194,70 @@ class Engine:
         _lib.check(self._L.ngp_ga_step(self._h, _p(genomes), _p(fitness), n, seed, generation, ctypes.byref(nz) if nz else None,
                                        _p(nxt), _p(parent), _p(invalid), _p(stats), _stream(self.device)), "ngp_ga_step")
         return {"genomes": nxt, "parent_idx": parent, "invalid": invalid, "stats": stats}
+
+    # ---- toolbox.select / mate / mutate as separate callables (ga.py:89-94) -------------------
+    def select(self, fitness: torch.Tensor, k: int, draws: torch.Tensor | None = None, seed: int = 0, generation: int = 0) -> torch.Tensor:
+        """selTournament(individuals, k, tournsize=TOURNAMENT_SIZE) -> winner indices i32[k]."""
+        self._check_tensor(fitness, torch.float64, "fitness")
+        if draws is not None:
+            self._check_tensor(draws, torch.int32, "draws")
+            assert tuple(draws.shape) == (k, max(1, self.config.TOURNAMENT_SIZE))
+        out = torch.empty(k, dtype=torch.int32, device=self.device)
+        _lib.check(self._L.ngp_select(self._h, _p(fitness), fitness.shape[0], k, _p(draws), seed, generation, _p(out), _stream(self.device)),
+                   "ngp_select")
+        return out
+
+    def mate(self, ind1: torch.Tensor, ind2: torch.Tensor, u: torch.Tensor | None = None, pair: int = 0, seed: int = 0, generation: int = 0):
+        """cxBlend(ind1, ind2, CROSSOVER_BLEND_ALPHA) in place."""
+        for t, nme in ((ind1, "ind1"), (ind2, "ind2")):
+            self._check_tensor(t, torch.float32, nme)
+            assert t.numel() == self.gene_size
+        if u is not None:
+            self._check_tensor(u, torch.float32, "u")
+        _lib.check(self._L.ngp_mate(self._h, _p(ind1), _p(ind2), _p(u), pair, seed, generation, _stream(self.device)), "ngp_mate")
+        return ind1, ind2
+
+    def mutate(self, ind: torch.Tensor, u: torch.Tensor | None = None, z: torch.Tensor | None = None, slot: int = 0, seed: int = 0,
+               generation: int = 0):
+        """mutGaussian(ind, mu, sigma, indpb) in place."""
+        self._check_tensor(ind, torch.float32, "ind")
+        assert ind.numel() == self.gene_size
+        _lib.check(self._L.ngp_mutate(self._h, _p(ind), _p(u), _p(z), slot, seed, generation, _stream(self.device)), "ngp_mutate")
+        return (ind,)
+
+    # ---- hall of fame --------------------------------------------------------------------------
+    def hof_update(self, hof_genomes: torch.Tensor, hof_fitness: torch.Tensor, n_hof: int, genomes: torch.Tensor, fitness: torch.Tensor) -> int:
+        """HallOfFame(maxsize).update(population) on device buffers [maxsize, G] / [maxsize]; returns the new member count."""
+        self._check_tensor(hof_genomes, torch.float32, "hof_genomes")
+        self._check_tensor(hof_fitness, torch.float64, "hof_fitness")
+        self._check_tensor(genomes, torch.float32, "genomes")
+        self._check_tensor(fitness, torch.float64, "fitness")
+        maxsize = hof_genomes.shape[0]
+        assert hof_fitness.shape[0] == maxsize and genomes.shape[0] == fitness.shape[0]
+        cnt = ctypes.c_int32(n_hof)
+        _lib.check(self._L.ngp_hof_update(self._h, _p(hof_genomes), _p(hof_fitness), ctypes.byref(cnt), maxsize, _p(genomes), _p(fitness),
+                                          genomes.shape[0], _stream(self.device)), "ngp_hof_update")
+        return int(cnt.value)
+
+    # ---- multi-GPU exchange records --------------------------------------------------------------
+    def exchange_bytes(self, n_max: int, k_max: int) -> int:
+        return int(self._L.ngp_exchange_bytes(self._h, n_max, k_max))
+
+    def pack_elites(self, genomes: torch.Tensor, fitness: torch.Tensor, k: int, n_max: int, k_max: int, out: torch.Tensor | None = None):
+        self._check_tensor(genomes, torch.float32, "genomes")
+        self._check_tensor(fitness, torch.float64, "fitness")
+        if out is None:
+            out = torch.zeros(self.exchange_bytes(n_max, k_max), dtype=torch.uint8, device=self.device)
+        _lib.check(self._L.ngp_pack_elites(self._h, _p(genomes), _p(fitness), genomes.shape[0], k, n_max, k_max, _p(out), _stream(self.device)),
+                   "ngp_pack_elites")
+        return out
+
+    def unpack_elites(self, gathered: torch.Tensor, world: int, n_max: int, k_max: int, n_total: int, k_total: int):
+        self._check_tensor(gathered, torch.uint8, "gathered")
+        assert gathered.numel() == world * self.exchange_bytes(n_max, k_max)
+        fit = torch.empty(n_total, dtype=torch.float64, device=self.device)
+        eg = torch.empty((k_total, self.gene_size), dtype=torch.float32, device=self.device)
+        ef = torch.empty(k_total, dtype=torch.float64, device=self.device)
+        _lib.check(self._L.ngp_unpack_elites(self._h, _p(gathered), world, n_max, k_max, _p(fit), _p(eg), _p(ef), _stream(self.device)),
+                   "ngp_unpack_elites")
+        return fit, eg, ef

@@ -1,53 +1,100 @@
-"""Multi-GPU plumbing: the population is sharded over ranks (one process per GPU); self-play
-pairings stay inside a shard; per generation the ranks exchange only the fitness vector
-(all-gather) and their best genomes (elite all-gather = every owner broadcasting its elites).
-This replaces the reference's scoop.futures.map scatter/gather (ga.py:83, main.py:165).
+"""Population sharding over the GPUs of one box and the per-generation exchange.
 
-All functions work on whatever backend the process group uses (NCCL on GPUs, gloo in CPU tests)."""
+The reference scatters individuals with ``toolbox.map = scoop.futures.map`` (ga.py:83), gathers every fitness on the
+master and lets eaSimple update one hall of fame from the whole population (main.py:165-170).  Here rank r owns a
+contiguous shard (``shard_bounds``); self-play pairings, selection, crossover and mutation stay inside the shard (island
+model); once per generation every rank contributes ONE fixed-size record -- its fitness values and its k best genomes,
+packed by ``ngp_pack_elites`` -- to a single NCCL all-gather.  The gathered records are unpacked on the device
+(``ngp_unpack_elites``) into the global fitness vector (statistics) and the merged elites, which every rank feeds to its
+hall of fame in the same order, so all ranks hold the same hall of fame.
+
+The all-gather is issued asynchronously on a side stream and consumed one generation later (``Exchange.start`` /
+``Exchange.finish``): a rank whose longest episode is short does not wait for the slowest rank inside the generation.
+torch.distributed is plumbing only (process group, the collective itself)."""
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
 
 def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
-    """Contiguous block partition of the population."""
-    base, rem = divmod(n_total, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+    """Contiguous shard [lo, hi) of rank `rank`; the first n_total % world ranks hold one genome more."""
+    base, extra = divmod(n_total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
 
 
-def local_elites(fitness: torch.Tensor, genomes: torch.Tensor, k: int):
-    """The k best local genomes, best first; ties keep the lower index first (stable)."""
-    k = min(k, fitness.numel())
-    order = torch.argsort(fitness, descending=True, stable=True)[:k]
-    return genomes.index_select(0, order), fitness.index_select(0, order), order
+def shard_sizes(n_total: int, world: int):
+    return [shard_bounds(n_total, world, r)[1] - shard_bounds(n_total, world, r)[0] for r in range(world)]
 
 
-def exchange_generation(fitness: torch.Tensor, genomes: torch.Tensor, k_elite: int):
-    """fitness f64[n_local], genomes f32[n_local, G] on this rank's device.
-    Returns (global_fitness f64[world*n_local], elite_genomes f32[world*k, G], elite_fitness f64[world*k])
-    identical on every rank; elites are merged best-first (ties: lower rank, then lower local index)."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        eg, ef, _ = local_elites(fitness, genomes, k_elite)
-        return fitness, eg, ef
-    world = dist.get_world_size()
-    n_local = fitness.numel()
-    global_fitness = torch.empty(world * n_local, dtype=fitness.dtype, device=fitness.device)
-    dist.all_gather_into_tensor(global_fitness, fitness.contiguous())
-    eg, ef, _ = local_elites(fitness, genomes, k_elite)
-    k = eg.shape[0]
-    all_g = torch.empty((world * k, genomes.shape[1]), dtype=genomes.dtype, device=genomes.device)
-    all_f = torch.empty(world * k, dtype=fitness.dtype, device=fitness.device)
-    dist.all_gather_into_tensor(all_g, eg.contiguous())
-    dist.all_gather_into_tensor(all_f, ef.contiguous())
-    order = torch.argsort(all_f, descending=True, stable=True)
-    return global_fitness, all_g.index_select(0, order), all_f.index_select(0, order)
+def elite_counts(n_total: int, world: int, k_total: int):
+    """How many elites each rank contributes: k_total // world (at least 1), never more than its shard."""
+    per = max(1, k_total // world) if k_total > 0 else 0
+    return [min(per, n) for n in shard_sizes(n_total, world)]
 
 
-def global_stats(global_fitness: torch.Tensor):
-    """avg / std (ddof=0) / min / max over the whole population (main.py:158-162)."""
-    f = global_fitness.double()
-    return f.mean().item(), f.std(unbiased=False).item(), f.min().item(), f.max().item()
+def gather_records(record: torch.Tensor, group=None, async_op: bool = False):
+    """All-gather one equally sized uint8 record per rank -> (gathered [world * len(record)], work handle or None).
+    Works on CUDA tensors (NCCL) and on CPU tensors (gloo: host-logic tests)."""
+    if not dist.is_initialized():
+        return record.clone(), None
+    world = dist.get_world_size(group)
+    gathered = torch.empty(world * record.numel(), dtype=record.dtype, device=record.device)
+    if record.is_cuda:
+        work = dist.all_gather_into_tensor(gathered, record, group=group, async_op=async_op)
+    else:
+        work = dist.all_gather(list(gathered.view(world, -1).unbind(0)), record, group=group, async_op=async_op)
+    return gathered, work
+
+
+class Exchange:
+    """Per-generation exchange of one rank: pack on the compute stream, all-gather on a side stream, unpack when consumed."""
+
+    def __init__(self, engine, n_total: int, k_total: int, group=None):
+        self.engine = engine
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_total = n_total
+        sizes = shard_sizes(n_total, self.world)
+        counts = elite_counts(n_total, self.world, k_total)
+        self.n_local, self.k_local = sizes[self.rank], counts[self.rank]
+        self.n_max, self.k_max = max(sizes), max(counts)
+        self.k_sum = sum(counts)
+        self.side = torch.cuda.Stream(device=engine.device)
+        self._pending = None
+
+    def start(self, genomes: torch.Tensor, fitness: torch.Tensor):
+        """Pack this rank's record (current stream) and launch the all-gather on the side stream."""
+        assert genomes.shape[0] == self.n_local and self._pending is None
+        record = self.engine.pack_elites(genomes, fitness, self.k_local, self.n_max, self.k_max)
+        ready = torch.cuda.Event()
+        ready.record()
+        record.record_stream(self.side)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            gathered, work = gather_records(record, self.group, async_op=True)
+        self._pending = (record, gathered, work)
+
+    def finish(self):
+        """Wait for the pending all-gather and unpack it (side stream).  Returns (fitness_all f64[N], elite_genomes
+        f32[sum k][G], elite_fitness f64[sum k]); the current stream is made to wait for the results."""
+        record, gathered, work = self._pending
+        self._pending = None
+        with torch.cuda.stream(self.side):
+            if work is not None:
+                work.wait()
+            out = self.engine.unpack_elites(gathered, self.world, self.n_max, self.k_max, self.n_total, self.k_sum)
+            done = torch.cuda.Event()
+            done.record()
+        torch.cuda.current_stream().wait_event(done)
+        for t in (record, gathered) + tuple(out):
+            t.record_stream(torch.cuda.current_stream())
+        return out
+
+    @property
+    def pending(self) -> bool:
+        return self._pending is not None

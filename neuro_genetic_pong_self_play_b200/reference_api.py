@@ -3,18 +3,20 @@
 Names and argument meaning follow the reference so its call sites read the same:
   NeuralNetwork(nodes, weights=..., bias=...).run(vec6)        numpy_nn.py:35-50, 120-137
   find_stuff(observation)                                      utils.py:14-19
-  evaluate(individual) -> (fitness,)                           main.py:28-66
-  toolbox.select / mate / mutate / map / evaluate              ga.py:83-94
-  run_generations(...)  (eaSimple-shaped loop + stats)         main.py:157-173
-  save_checkpoint / load_latest_population                     utils.py:116-125, ga.py:32-53
-Every call lands in libngp.so's CUDA kernels through Engine; nothing here computes on the CPU except
-list/array marshalling and the hall-of-fame bookkeeping (a few hundred comparisons per generation)."""
+  toolbox.evaluate(individual) -> (fitness,)                   main.py:28-66
+  toolbox.map / select / mate / mutate / clone / population    ga.py:83-94
+  HallOfFame(maxsize).update(population)                       ga.py:78 (DEAP tools.HallOfFame)
+  run_generations(...)  (eaSimple-shaped loop + logbook)       main.py:157-173
+  save_checkpoint / load_latest_population                     utils.py:116-125, ga.py:13-53
+Every call lands in libngp.so's CUDA kernels through Engine; nothing here computes on the CPU except argument
+marshalling (individuals are rows of device tensors instead of Python lists)."""
 from __future__ import annotations
 
 import glob
 import os
 import time
-from typing import List, Optional, Sequence
+import warnings
+from typing import Optional, Sequence
 
 import numpy as np
 import torch
@@ -48,7 +50,8 @@ class NeuralNetwork:
         need = cfg.gene_size()
         if len(g) < need:
             raise ValueError(f"need {need} weights, got {len(g)}")
-        # populate_weights tolerates extra genes with a warning (numpy_nn.py:66-67)
+        if len(g) > need:                                   # populate_weights only warns (numpy_nn.py:66-67)
+            warnings.warn("There are extra weights that were not used (numpy_nn.py:66-67)")
         self._genome = torch.from_numpy(np.ascontiguousarray(g[:need])).to(self._eng.device).reshape(1, need)
 
     def run(self, input_vector):
@@ -69,133 +72,240 @@ def find_stuff(observation: np.ndarray, engine: Engine | None = None):
 
 
 class HallOfFame:
-    """deap.tools.HallOfFame(maxsize) semantics: best distinct individuals ever seen, best first."""
+    """deap.tools.HallOfFame(maxsize): the best distinct individuals ever seen, best first -- resident on the device
+    (ngp_hof_update).  The reference's in-place random.shuffle of `items` (utils.py:93-95) is not reproduced: members stay
+    sorted and an opponent is drawn by index."""
 
-    def __init__(self, maxsize: int):
-        self.maxsize = maxsize
-        self.genomes: List[np.ndarray] = []
-        self.fitness: List[float] = []
+    def __init__(self, maxsize: int, engine: Engine):
+        self.maxsize = int(maxsize)
+        self.engine = engine
+        self.genomes = torch.zeros((max(1, self.maxsize), engine.gene_size), dtype=torch.float32, device=engine.device)
+        self.fitness = torch.zeros(max(1, self.maxsize), dtype=torch.float64, device=engine.device)
+        self.n = 0
 
     def __len__(self):
-        return len(self.genomes)
+        return self.n
 
-    def update(self, genomes: np.ndarray, fitness: np.ndarray):
-        if self.maxsize == 0:
+    def clear(self):
+        self.n = 0
+
+    def update(self, genomes: torch.Tensor, fitness: torch.Tensor):
+        if self.maxsize == 0 or genomes.shape[0] == 0:
             return
-        # only candidates that can enter: better than the current worst or while not full
-        order = range(len(fitness))
-        for i in order:
-            f = float(fitness[i])
-            if len(self.genomes) == 0:
-                self.genomes.append(genomes[i].copy()); self.fitness.append(f)
-                continue
-            if f > self.fitness[-1] or len(self.genomes) < self.maxsize:
-                if any(np.array_equal(genomes[i], h) for h in self.genomes):
-                    continue
-                if len(self.genomes) >= self.maxsize:
-                    self.genomes.pop(); self.fitness.pop()
-                pos = 0
-                while pos < len(self.fitness) and self.fitness[pos] > f:
-                    pos += 1
-                self.genomes.insert(pos, genomes[i].copy()); self.fitness.insert(pos, f)
+        self.n = self.engine.hof_update(self.genomes[: self.maxsize], self.fitness[: self.maxsize], self.n, genomes.contiguous(),
+                                        fitness.contiguous())
 
-    def tensors(self, device):
-        if not self.genomes:
+    def tensors(self, device=None):
+        """(genomes [n, G], fitness [n]) views of the members, or (None, None) when empty."""
+        if self.n == 0:
             return None, None
-        return (torch.from_numpy(np.stack(self.genomes)).to(device), torch.tensor(self.fitness, dtype=torch.float64, device=device))
+        return self.genomes[: self.n], self.fitness[: self.n]
+
+    @property
+    def items(self):
+        """Host copy of the members as lists of genes, best first (DEAP's HallOfFame.items)."""
+        return [row.tolist() for row in self.genomes[: self.n].cpu()]
+
+    @property
+    def keys(self):
+        """Member fitness values, best first (DEAP keeps them ascending; only inspection uses this)."""
+        return self.fitness[: self.n].cpu().tolist()
+
+    def load(self, genomes: np.ndarray, fitness: np.ndarray):
+        n = min(len(fitness), self.maxsize)
+        self.n = n
+        if n:
+            self.genomes[:n] = torch.from_numpy(np.ascontiguousarray(genomes[:n], np.float32)).to(self.engine.device)
+            self.fitness[:n] = torch.from_numpy(np.ascontiguousarray(fitness[:n], np.float64)).to(self.engine.device)
 
 
 class Toolbox:
-    """The slice of the DEAP toolbox the reference registers (ga.py:83-94), on device tensors."""
+    """The slice of the DEAP toolbox the reference registers (ga.py:83-94), on device tensors: an individual is a row
+    f32[G], a population a tensor f32[N][G], fitness a tensor f64[N]."""
 
     def __init__(self, config: Config | None = None, engine: Engine | None = None, seed: int = 0):
         self.config = config or Config()
         self.engine = engine or get_engine(self.config)
         self.seed = seed
         self.generation = 0
-        self.hall_of_fame = HallOfFame(self.config.HALL_OF_FAME_AMOUNT)
+        self.hall_of_fame = HallOfFame(self.config.HALL_OF_FAME_AMOUNT, self.engine)
+        self.last_frames = 0
 
-    def population(self, n: int) -> torch.Tensor:
-        return self.engine.init_population(n, seed=self.seed)
+    # ---- toolbox.population / individual / clone (ga.py:85-87) ----
+    def population(self, n: int, seed: int | None = None) -> torch.Tensor:
+        return self.engine.init_population(n, seed=self.seed if seed is None else seed)
 
+    def individual(self) -> torch.Tensor:
+        return self.engine.init_population(1, seed=self.seed + 0x9E3779B9 * (self.generation + 1))[0]
+
+    @staticmethod
+    def clone(t: torch.Tensor) -> torch.Tensor:
+        return t.clone()
+
+    # ---- toolbox.evaluate / toolbox.map (main.py:28-66, ga.py:83) ----
     def evaluate(self, individual, render=False):
         """main.evaluate for ONE individual -> 1-tuple (main.py:66)."""
-        g = torch.tensor(np.asarray(individual, np.float32).reshape(1, -1), device=self.engine.device)
+        if isinstance(individual, torch.Tensor):
+            g = individual.to(self.engine.device, torch.float32).reshape(1, -1).contiguous()
+        else:
+            g = torch.tensor(np.asarray(individual, np.float32).reshape(1, -1), device=self.engine.device)
         return (float(self.map_evaluate(g)[0].item()),)
 
-    def map_evaluate(self, genomes: torch.Tensor) -> torch.Tensor:
-        """toolbox.map(toolbox.evaluate, population): one fused launch for the whole population."""
-        hg, hf = self.hall_of_fame.tensors(self.engine.device)
-        out = self.engine.evaluate(genomes, hg, hf, seed=self.seed, generation=self.generation)
-        self.last_frames = out["frames_total"]
+    def map(self, fn, individuals):
+        """toolbox.map(toolbox.evaluate, individuals) is ONE fused launch; any other function maps as usual."""
+        if getattr(fn, "__func__", None) is Toolbox.evaluate and getattr(fn, "__self__", None) is self:
+            if isinstance(individuals, torch.Tensor):
+                g = individuals
+            else:
+                g = torch.tensor(np.asarray(list(individuals), np.float32), device=self.engine.device)
+            return [(float(f),) for f in self.map_evaluate(g.contiguous()).cpu().tolist()]
+        return map(fn, individuals)
+
+    def map_evaluate(self, genomes: torch.Tensor, sync: bool = True) -> torch.Tensor:
+        """Fitness tensor f64[N] of a whole population (device in, device out)."""
+        hg, hf = self.hall_of_fame.tensors()
+        out = self.engine.evaluate(genomes, hg, hf, seed=self.seed, generation=self.generation, sync=sync)
+        if sync:
+            self.last_frames = out["frames_total"]
         return out["fitness"]
 
-    def vary(self, genomes: torch.Tensor, fitness: torch.Tensor):
-        """toolbox.select + varAnd(mate, mutate) as one GA step."""
-        return self.engine.ga_step(genomes, fitness, seed=self.seed, generation=self.generation)
+    # ---- toolbox.select / mate / mutate (ga.py:89-94) ----
+    def select(self, genomes: torch.Tensor, fitness: torch.Tensor, k: int | None = None, draws: torch.Tensor | None = None):
+        """selTournament(population, k, tournsize=TOURNAMENT_SIZE) -> (the k selected individuals (copies), their indices)."""
+        k = genomes.shape[0] if k is None else k
+        idx = self.engine.select(fitness, k, draws, seed=self.seed, generation=self.generation)
+        return genomes.index_select(0, idx.long()), idx
+
+    def mate(self, ind1: torch.Tensor, ind2: torch.Tensor, u: torch.Tensor | None = None, pair: int = 0):
+        """cxBlend in place on two individuals (rows of a population tensor work: they are contiguous views)."""
+        return self.engine.mate(ind1, ind2, u, pair, seed=self.seed, generation=self.generation)
+
+    def mutate(self, ind: torch.Tensor, u: torch.Tensor | None = None, z: torch.Tensor | None = None, slot: int = 0):
+        """mutGaussian in place on one individual; returns a 1-tuple like DEAP."""
+        return self.engine.mutate(ind, u, z, slot, seed=self.seed, generation=self.generation)
+
+    def vary(self, genomes: torch.Tensor, fitness: torch.Tensor, noise: dict | None = None):
+        """toolbox.select + varAnd(mate, mutate) as one fused GA step."""
+        return self.engine.ga_step(genomes, fitness, seed=self.seed, generation=self.generation, noise=noise)
 
 
-def run_generations(toolbox: Toolbox, genomes: torch.Tensor, ngen: int, fitness: Optional[torch.Tensor] = None, verbose: bool = True):
-    """deap.algorithms.eaSimple as the reference drives it (main.py:165-170): evaluate, update the hall of
-    fame, then ngen x (select, vary, evaluate the invalid, update hall of fame, log avg/std/min/max)."""
+def _stats_row(gen, nevals, fit, frames, t0):
+    f = fit.double()
+    return dict(gen=gen, nevals=int(nevals), avg=f.mean().item(), std=f.std(unbiased=False).item(), min=f.min().item(),
+                max=f.max().item(), frames=int(frames), seconds=time.time() - t0)
+
+
+def run_generations(toolbox: Toolbox, genomes: torch.Tensor, ngen: int, fitness: Optional[torch.Tensor] = None, verbose: bool = True,
+                    exchange=None, noise_fn=None):
+    """deap.algorithms.eaSimple as the reference drives it (main.py:165-170): evaluate the invalid individuals, update the
+    hall of fame, then ngen x (select, varAnd, evaluate the invalid offspring, update the hall of fame, log
+    gen/nevals/avg/std/min/max).
+
+    fitness: None = nobody evaluated yet; otherwise f64[N] with NaN marking invalid individuals (a topped-up checkpoint).
+    exchange: a parallel.Exchange when the population is sharded over several ranks (`genomes` is then this rank's shard):
+    selection and variation stay inside the shard; the hall of fame is fed the merged elites of all ranks and the logbook
+    rows describe the whole population, both one generation late (the all-gather of generation g is consumed while
+    generation g+1 is being played, so no rank waits for another inside a generation).
+    noise_fn(generation) -> dict: injected GA noise (parity tests)."""
     log = []
+    sharded = exchange is not None and exchange.world > 1
+    pending = None          # (gen, nevals, frames, t0) of the generation whose exchange is in flight
 
-    def record(gen, nevals, fit, t0):
-        f = fit.double()
-        row = dict(gen=gen, nevals=int(nevals), avg=f.mean().item(), std=f.std(unbiased=False).item(), min=f.min().item(),
-                   max=f.max().item(), frames=toolbox.last_frames, seconds=time.time() - t0)
+    def emit(row):
         log.append(row)
         if verbose:
-            print("{gen}\t{nevals}\t{avg:.6g}\t{std:.6g}\t{min:.6g}\t{max:.6g}".format(**row))
+            print("{gen}\t{nevals}\t{avg:.6g}\t{std:.6g}\t{min:.6g}\t{max:.6g}".format(**row), flush=True)
+
+    def consume():
+        nonlocal pending
+        if pending is None:
+            return
+        fit_all, eg, ef = exchange.finish()
+        toolbox.hall_of_fame.update(eg, ef)
+        gen, nevals, frames, t0 = pending
+        pending = None
+        emit(_stats_row(gen, nevals, fit_all, frames, t0))
+
+    def after_evaluate(gen, nevals, t0):
+        nonlocal pending
+        if sharded:
+            consume()                                    # generation gen-1's exchange: hall of fame + logbook row
+            exchange.start(genomes, fitness)
+            pending = (gen, nevals, toolbox.last_frames, t0)
+        else:
+            toolbox.hall_of_fame.update(genomes, fitness)
+            emit(_stats_row(gen, nevals, fitness, toolbox.last_frames, t0))
 
     t0 = time.time()
-    if fitness is None:
-        fitness = toolbox.map_evaluate(genomes)
-        toolbox.hall_of_fame.update(genomes.cpu().numpy(), fitness.cpu().numpy())
-        record(0, genomes.shape[0], fitness, t0)
+    if fitness is None or bool(torch.isnan(fitness).any()):
+        evaluated = toolbox.map_evaluate(genomes)
+        if fitness is None:
+            nevals, fitness = genomes.shape[0], evaluated
+        else:
+            invalid = torch.isnan(fitness)
+            nevals, fitness = int(invalid.sum().item()), torch.where(invalid, evaluated, fitness)
+        after_evaluate(toolbox.generation, nevals, t0)
     for _ in range(ngen):
         toolbox.generation += 1
         t0 = time.time()
-        nxt = toolbox.vary(genomes, fitness)
+        nxt = toolbox.vary(genomes, fitness, noise_fn(toolbox.generation) if noise_fn else None)
         children, invalid, parents = nxt["genomes"], nxt["invalid"].bool(), nxt["parent_idx"].long()
         evaluated = toolbox.map_evaluate(children)
         # eaSimple re-evaluates only individuals whose fitness was invalidated; clones keep their parent's
         fitness = torch.where(invalid, evaluated, fitness.index_select(0, parents))
         genomes = children
-        toolbox.hall_of_fame.update(genomes.cpu().numpy(), fitness.cpu().numpy())
-        record(toolbox.generation, int(invalid.sum().item()), fitness, t0)
+        after_evaluate(toolbox.generation, int(invalid.sum().item()), t0)
+    if sharded:
+        consume()
     return genomes, fitness, log
 
 
 # ---- checkpoint / resume (utils.py:116-125, ga.py:13-53) -------------------------------------------
+# Layout: one .npz per checkpoint (population, fitness, hall of fame, Philox seed + generation counter = the RNG state,
+# network_shape, bias).  The reference pickles DEAP objects (deap.creator.Individual, tools.HallOfFame) that cannot be
+# unpickled without DEAP; those files are NOT read here (a warning is printed when only such files are present).
 def save_checkpoint(toolbox: Toolbox, genomes: torch.Tensor, fitness: torch.Tensor, directory: str = "checkpoints/checkpoints") -> str:
     os.makedirs(directory, exist_ok=True)
     path = os.path.join(directory, "c_{}.npz".format(time.strftime("%H_%M_%S")))
+    k = 1
+    while os.path.exists(path):                          # two saves within one second (the reference would overwrite)
+        path = os.path.join(directory, "c_{}_{}.npz".format(time.strftime("%H_%M_%S"), k)); k += 1
     hof = toolbox.hall_of_fame
+    hg, hf = hof.tensors()
     np.savez(path, population=genomes.cpu().numpy(), fitness=fitness.cpu().numpy(),
-             hof_genomes=np.stack(hof.genomes) if len(hof) else np.zeros((0, genomes.shape[1]), np.float32),
-             hof_fitness=np.asarray(hof.fitness, np.float64), seed=np.uint64(toolbox.seed), generation=np.uint64(toolbox.generation),
-             network_shape=np.asarray(toolbox.config.NETWORK_SHAPE, np.int32))
+             hof_genomes=hg.cpu().numpy() if hg is not None else np.zeros((0, genomes.shape[1]), np.float32),
+             hof_fitness=hf.cpu().numpy() if hf is not None else np.zeros(0, np.float64), seed=np.uint64(toolbox.seed),
+             generation=np.uint64(toolbox.generation), network_shape=np.asarray(toolbox.config.NETWORK_SHAPE, np.int32),
+             bias=np.int32(1 if toolbox.config.BIAS else 0))
     return path
 
 
 def load_latest_population(toolbox: Toolbox, directory: str = "checkpoints/checkpoints"):
-    """Newest checkpoint by ctime (ga.py:32-38), sorted by fitness descending (ga.py:45), truncated or
-    topped up with fresh random individuals to POPULATION_SIZE (ga.py:13-29).  Returns (genomes, fitness|None)."""
+    """Newest checkpoint by ctime (ga.py:32-38), sorted by fitness descending (ga.py:45), truncated or topped up with fresh
+    random individuals to POPULATION_SIZE (ga.py:13-29).  Returns (genomes, fitness); fitness is None without a checkpoint
+    and holds NaN for topped-up (never evaluated) individuals -- loaded individuals keep their fitness, as in the reference."""
     files = glob.glob(os.path.join(directory, "*.npz"))
     n = toolbox.config.POPULATION_SIZE
     if not files:
+        others = glob.glob(os.path.join(directory, "*"))
+        if others:
+            warnings.warn(f"{len(others)} file(s) in {directory} are not .npz checkpoints of this package (the reference's "
+                          "pickles need DEAP to load) and are ignored")
         return toolbox.population(n), None
     cp = np.load(max(files, key=os.path.getctime))
     if tuple(int(v) for v in cp["network_shape"]) != tuple(toolbox.config.NETWORK_SHAPE):
         raise _lib.NgpError("checkpoint network_shape differs from the configured NETWORK_SHAPE; rebuild the Toolbox with it")
+    if "bias" in cp and bool(int(cp["bias"])) != bool(toolbox.config.BIAS):
+        raise _lib.NgpError("checkpoint BIAS differs from the configured BIAS")
     order = np.argsort(-cp["fitness"], kind="stable")
     pop, fit = cp["population"][order][:n], cp["fitness"][order][:n]
     toolbox.seed = int(cp["seed"]); toolbox.generation = int(cp["generation"])
-    toolbox.hall_of_fame.genomes = [g for g in cp["hof_genomes"]]; toolbox.hall_of_fame.fitness = [float(f) for f in cp["hof_fitness"]]
+    toolbox.hall_of_fame.load(cp["hof_genomes"], cp["hof_fitness"])
     dev = toolbox.engine.device
-    genomes = torch.from_numpy(pop).to(dev)
+    genomes = torch.from_numpy(np.ascontiguousarray(pop)).to(dev)
+    fitness = torch.from_numpy(np.ascontiguousarray(fit)).to(dev)
     if len(pop) < n:
-        fresh = toolbox.engine.init_population(n - len(pop), seed=toolbox.seed + 1 + toolbox.generation)
-        return torch.cat([genomes, fresh]), None
-    return genomes, torch.from_numpy(fit).to(dev)
+        fresh = toolbox.population(n - len(pop), seed=toolbox.seed + 1 + toolbox.generation)
+        genomes = torch.cat([genomes, fresh])
+        fitness = torch.cat([fitness, torch.full((n - len(pop),), float("nan"), dtype=torch.float64, device=dev)])
+    return genomes, fitness

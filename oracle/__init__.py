@@ -91,17 +91,20 @@ def lib():
         L.eo_find_stuff.argtypes = [vp, ctypes.POINTER(Obs)]
         L.eo_clamp.restype = ctypes.c_int; L.eo_clamp.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_int]
         L.eo_reward.restype = ctypes.c_double; L.eo_reward.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int]
-        L.eo_philox_bit.restype = ctypes.c_uint32; L.eo_philox_bit.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
+        L.eo_philox_bit.restype = ctypes.c_uint32; L.eo_philox_bit.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
         L.eo_philox4x32.argtypes = [vp, vp, vp]
-        L.eo_action_to_input.argtypes = [vp, ctypes.POINTER(Input)]
+        L.eo_bot_act.restype = ctypes.c_int; L.eo_bot_act.argtypes = [ctypes.c_int, vp, ctypes.c_int, ctypes.c_int]
+        L.eo_inference_vector.argtypes = [vp, vp, ctypes.c_double, ctypes.c_double, vp]
+        L.eo_action_to_input.argtypes = [vp, ctypes.c_int, ctypes.POINTER(Input)]
         L.eo_reset_to_state.argtypes = [vp, ctypes.c_int]
-        L.eo_episode.argtypes = [vp, ctypes.POINTER(Shape), Policy, Policy, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint32,
-                                 ctypes.c_int, ctypes.POINTER(EpisodeResult), vp, ctypes.c_int]
+        L.eo_set_button_map.argtypes = [vp]; L.eo_get_button_map.argtypes = [vp]
+        L.eo_episode.argtypes = [vp, ctypes.POINTER(Shape), Policy, Policy, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64,
+                                 ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.POINTER(EpisodeResult), vp, ctypes.c_int]
         L.eo_evaluate.restype = ctypes.c_double
         L.eo_evaluate.argtypes = [ctypes.c_char_p, ctypes.POINTER(Shape), vp, vp, vp, ctypes.c_int, vp, ctypes.c_uint64,
-                                  ctypes.c_uint32, vp, vp]
-        L.eo_selfplay_game.argtypes = [ctypes.c_char_p, ctypes.POINTER(Shape), vp, vp, ctypes.c_uint64, ctypes.c_uint32,
-                                       ctypes.POINTER(EpisodeResult)]
+                                  ctypes.c_uint64, ctypes.c_uint32, vp, vp]
+        L.eo_selfplay_game.argtypes = [ctypes.c_char_p, ctypes.POINTER(Shape), vp, vp, ctypes.c_uint64, ctypes.c_uint64,
+                                       ctypes.c_uint32, ctypes.POINTER(EpisodeResult)]
         _lib = L
     return _lib
 
@@ -134,6 +137,7 @@ class Atari:
 
     def reset_to_state(self, state_id: int):
         lib().eo_reset_to_state(self._h, state_id)
+        self.players = 1 if state_id == STATE_START_1P else 2       # main.py:40 makes the robot game with players=1
 
     def run_frame(self, swchb=0x3F, fire=0, dec=0, inc=0, want_frame=True):
         fb = np.zeros((210, 160), np.uint8) if want_frame else None
@@ -146,7 +150,7 @@ class Atari:
     def step(self, action16, want_frame=True):
         a = np.ascontiguousarray(action16, dtype=np.uint8)
         inp = Input()
-        lib().eo_action_to_input(_ptr(a), ctypes.byref(inp))
+        lib().eo_action_to_input(_ptr(a), int(getattr(self, "players", 2)), ctypes.byref(inp))
         return self.run_frame(inp.swchb, inp.fire, inp.dec, inp.inc, want_frame)
 
     @property
@@ -173,7 +177,7 @@ class Atari:
     def instructions(self) -> int:
         return int(lib().a26o_instructions(self._h))
 
-    def episode(self, shape: Shape, left, right, mult=1.0, seed=0, env_id=0, max_frames=0, trace_cap=0):
+    def episode(self, shape: Shape, left, right, mult=1.0, seed=0, env_id=0, max_frames=0, trace_cap=0, generation=0, players=None):
         """left/right: ("hardcoded"|"score", None) or ("mlp", float32 genome)."""
         keep = []
 
@@ -187,9 +191,23 @@ class Atari:
 
         res = EpisodeResult()
         trace = np.zeros((max(trace_cap, 1), TRACE_BYTES), np.uint8)
-        lib().eo_episode(self._h, ctypes.byref(shape), pol(left), pol(right), float(mult), int(seed), int(env_id),
-                         int(max_frames), ctypes.byref(res), _ptr(trace) if trace_cap else None, trace_cap)
+        if players is None:
+            players = int(getattr(self, "players", 2))
+        lib().eo_episode(self._h, ctypes.byref(shape), pol(left), pol(right), float(mult), int(seed), int(generation), int(env_id),
+                         int(players), int(max_frames), ctypes.byref(res), _ptr(trace) if trace_cap else None, trace_cap)
         return res, trace[: min(res.frames, trace_cap)]
+
+
+def button_map() -> np.ndarray:
+    m = np.zeros(16, np.uint8)
+    lib().eo_get_button_map(_ptr(m))
+    return m
+
+
+def set_button_map(m):
+    m = np.ascontiguousarray(m, np.uint8)
+    assert m.shape == (16,)
+    lib().eo_set_button_map(_ptr(m))
 
 
 def fb_to_rgb(fb: np.ndarray) -> np.ndarray:
@@ -229,6 +247,17 @@ def mlp_forward(nodes, genome, x, bias=True):
     return out, act.value
 
 
+def bot_act(kind: int, x, score1: int = 0, score2: int = 0) -> int:
+    xv = np.ascontiguousarray(x, np.float64)
+    return int(lib().eo_bot_act(kind, _ptr(xv), score1, score2))
+
+
+def inference_vector(ball, last, me_row: float, enemy_row: float) -> np.ndarray:
+    b = np.ascontiguousarray(ball, np.float64); l = np.ascontiguousarray(last, np.float64); out = np.zeros(6, np.float64)
+    lib().eo_inference_vector(_ptr(b), _ptr(l), float(me_row), float(enemy_row), _ptr(out))
+    return out
+
+
 def det_exp(x: float) -> float:
     return lib().eo_det_exp(float(x))
 
@@ -239,7 +268,7 @@ def philox4x32(ctr, key) -> np.ndarray:
     return o
 
 
-def evaluate(nodes, genome, hof_genomes=None, hof_fitness=None, hof_pick=(0, 0, 0), seed=0, genome_id=0, bias=True):
+def evaluate(nodes, genome, hof_genomes=None, hof_fitness=None, hof_pick=(0, 0, 0), seed=0, genome_id=0, bias=True, generation=0):
     sh = Shape.make(nodes, bias)
     g = np.ascontiguousarray(genome, np.float32)
     n_hof = 0 if hof_genomes is None else len(hof_genomes)
@@ -248,15 +277,15 @@ def evaluate(nodes, genome, hof_genomes=None, hof_fitness=None, hof_pick=(0, 0, 
     pick = np.ascontiguousarray(hof_pick, np.int32)
     rewards = np.zeros(GAMES_TO_PLAY, np.float64); frames = np.zeros(GAMES_TO_PLAY, np.int32)
     fit = lib().eo_evaluate(load_rom(), ctypes.byref(sh), _ptr(g), _ptr(hg), _ptr(hf), n_hof, _ptr(pick), int(seed),
-                            int(genome_id), _ptr(rewards), _ptr(frames))
+                            int(generation), int(genome_id), _ptr(rewards), _ptr(frames))
     return fit, rewards, frames
 
 
-def selfplay_game(nodes, right, left, seed=0, env_id=0, bias=True):
+def selfplay_game(nodes, right, left, seed=0, env_id=0, bias=True, generation=0):
     sh = Shape.make(nodes, bias)
     r = np.ascontiguousarray(right, np.float32); l = np.ascontiguousarray(left, np.float32)
     res = EpisodeResult()
-    lib().eo_selfplay_game(load_rom(), ctypes.byref(sh), _ptr(r), _ptr(l), int(seed), int(env_id), ctypes.byref(res))
+    lib().eo_selfplay_game(load_rom(), ctypes.byref(sh), _ptr(r), _ptr(l), int(seed), int(generation), int(env_id), ctypes.byref(res))
     return res
 
 
@@ -339,3 +368,103 @@ def hall_of_fame_update(hof_genomes, hof_fitness, pop, fitness, maxsize):
                 pos += 1
             hof_g.insert(pos, g.copy()); hof_f.insert(pos, float(f))
     return hof_g, hof_f
+
+
+# ----------------------------------------------------------------------------------------
+# Restatement of the multi-GPU exchange record (include/ngp.h: ngp_pack_elites / ngp_unpack_elites):
+#   [ n_local i32 | k_local i32 | 8 B pad | fitness f64[n_max] | elite_fitness f64[k_max] | elite_genomes f32[k_max][G] ]
+# padded to a multiple of 16 bytes.  Elites = the k best of the shard, best first, ties by lower index.
+# ----------------------------------------------------------------------------------------
+def exchange_bytes(n_max: int, k_max: int, G: int) -> int:
+    raw = 16 + n_max * 8 + k_max * 8 + k_max * G * 4
+    return (raw + 15) & ~15
+
+
+def pack_record(genomes: np.ndarray, fitness: np.ndarray, k: int, n_max: int, k_max: int) -> np.ndarray:
+    n, G = genomes.shape
+    rec = np.zeros(exchange_bytes(n_max, k_max, G), np.uint8)
+    rec[:8] = np.array([n, k], np.int32).view(np.uint8)
+    order = np.argsort(-np.asarray(fitness, np.float64), kind="stable")[:k]
+    f = np.zeros(n_max, np.float64); f[:n] = fitness
+    ef = np.zeros(k_max, np.float64); ef[:k] = np.asarray(fitness, np.float64)[order]
+    eg = np.zeros((k_max, G), np.float32); eg[:k] = genomes[order]
+    o = 16
+    rec[o:o + n_max * 8] = f.view(np.uint8); o += n_max * 8
+    rec[o:o + k_max * 8] = ef.view(np.uint8); o += k_max * 8
+    rec[o:o + k_max * G * 4] = eg.reshape(-1).view(np.uint8)
+    return rec
+
+
+def unpack_records(gathered: np.ndarray, world: int, n_max: int, k_max: int, G: int):
+    size = exchange_bytes(n_max, k_max, G)
+    fit, eg, ef = [], [], []
+    for r in range(world):
+        rec = np.ascontiguousarray(gathered[r * size:(r + 1) * size])
+        n, k = rec[:8].view(np.int32)
+        o = 16
+        fit.append(rec[o:o + n_max * 8].view(np.float64)[:n]); o += n_max * 8
+        ef.append(rec[o:o + k_max * 8].view(np.float64)[:k]); o += k_max * 8
+        eg.append(rec[o:o + k_max * G * 4].view(np.float32).reshape(k_max, G)[:k])
+    return np.concatenate(fit), np.concatenate(eg), np.concatenate(ef)
+
+
+# ----------------------------------------------------------------------------------------
+# Restatement of the product's Philox4x32-10 counter layouts (csrc/ga_streams.cuh, rollout.cuh plan_env): the noise the
+# CUDA kernels draw when none is injected.  Vectorised numpy Philox, pinned to the C one (and so to the Random123 KATs).
+# ----------------------------------------------------------------------------------------
+STREAM_SELECT, STREAM_CXDO, STREAM_CXU, STREAM_MUTDO = 0x53454C31, 0x43584431, 0x43585531, 0x4D544431
+STREAM_MUTU, STREAM_MUTZ, STREAM_INIT, STREAM_HOF = 0x4D545531, 0x4D545A31, 0x494E4931, 0x484F4621
+
+
+def philox4x32_np(c0, c1, c2, c3, seed: int):
+    """Vectorised Philox4x32-10: counters are broadcastable integer arrays, key = (seed lo, seed hi); returns 4 uint32 arrays."""
+    c0, c1, c2, c3 = np.broadcast_arrays(*(np.asarray(c, np.uint64) & 0xFFFFFFFF for c in (c0, c1, c2, c3)))
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    M0, M1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c0; p1 = M1 * c2
+        n0 = (p1 >> np.uint64(32)) ^ c1 ^ k0; n1 = p1 & mask
+        n2 = (p0 >> np.uint64(32)) ^ c3 ^ k1; n3 = p0 & mask
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask; k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
+
+
+def _u01(words):
+    return ((words >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)).astype(np.float32)
+
+
+def init_population_philox(n: int, G: int, seed: int) -> np.ndarray:
+    total = n * G
+    q = np.arange((total + 3) // 4, dtype=np.uint64)
+    w = np.stack(philox4x32_np(q & 0xFFFFFFFF, q >> np.uint64(32), 0, STREAM_INIT, seed), axis=1).reshape(-1)[:total]
+    return _u01(w).reshape(n, G)
+
+
+def ga_noise_philox(n: int, G: int, T: int, seed: int, generation: int, cxpb: float, mutpb: float):
+    """The noise ngp_ga_step draws for (seed, generation): same keys as the injected-noise interface (ngp_noise)."""
+    gen = generation & 0xFFFFFFFF
+    nb = (T + 3) // 4
+    slot = np.arange(n, dtype=np.uint64)[:, None]; blk = np.arange(nb, dtype=np.uint64)[None, :]
+    w = np.stack(philox4x32_np(slot, blk, gen, STREAM_SELECT, seed), axis=2).reshape(n, nb * 4)[:, :T]
+    sel = ((w.astype(np.uint64) * np.uint64(n)) >> np.uint64(32)).astype(np.int32)
+    pairs = n // 2
+    cx_do = (_u01(philox4x32_np(np.arange(pairs, dtype=np.uint64), 0, gen, STREAM_CXDO, seed)[0]) < np.float32(cxpb)).astype(np.uint8)
+    gb = (G + 3) // 4
+    pr = np.arange(pairs, dtype=np.uint64)[:, None]; gq = np.arange(gb, dtype=np.uint64)[None, :]
+    cx_u = _u01(np.stack(philox4x32_np(pr, gq, gen, STREAM_CXU, seed), axis=2).reshape(pairs, gb * 4)[:, :G])
+    ind = np.arange(n, dtype=np.uint64)
+    mut_do = (_u01(philox4x32_np(ind, 0, gen, STREAM_MUTDO, seed)[0]) < np.float32(mutpb)).astype(np.uint8)
+    mut_u = _u01(np.stack(philox4x32_np(ind[:, None], gq, gen, STREAM_MUTU, seed), axis=2).reshape(n, gb * 4)[:, :G])
+    z0, z1, _, _ = philox4x32_np(ind[:, None], np.arange(G, dtype=np.uint64)[None, :], gen, STREAM_MUTZ, seed)
+    u1 = ((z0 >> np.uint32(8)).astype(np.float64) + 1.0) / 16777216.0
+    u2 = _u01(z1).astype(np.float64)
+    mut_z = (np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)).astype(np.float32)       # the kernel: sqrtf, logf, cospif
+    return dict(sel_draws=sel, cx_do=cx_do, cx_u=cx_u, mut_do=mut_do, mut_u=mut_u, mut_z=mut_z)
+
+
+def hof_pick_philox(n: int, n_hof: int, seed: int, generation: int) -> np.ndarray:
+    """Hall-of-fame opponents ngp_evaluate draws for games 3..5 of genome g: counter (g, game, generation, 'HOF!')."""
+    g = np.arange(n, dtype=np.uint64)[:, None]; k = np.arange(3, 6, dtype=np.uint64)[None, :]
+    w = philox4x32_np(g, k, generation & 0xFFFFFFFF, STREAM_HOF, seed)[0]
+    return (w % np.uint32(n_hof)).astype(np.int32)

@@ -130,22 +130,46 @@ void eo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]
 }
 
 /* the reference's np.random.choice(2) per player per frame (utils.py:112-113, main.py:139-140),
- * made reproducible: counter = (env, frame, stream, 0), key = seed */
-uint32_t eo_philox_bit(uint64_t seed, uint32_t env_id, uint32_t frame, uint32_t stream)
+ * made reproducible: counter = (env, frame, 2*generation + player, 'PONG'), key = seed */
+uint32_t eo_philox_bit(uint64_t seed, uint64_t generation, uint32_t env_id, uint32_t frame, uint32_t stream)
 {
-    uint32_t ctr[4] = {env_id, frame, stream, 0x504F4E47u}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, out[4];
+    uint32_t ctr[4] = {env_id, frame, ((uint32_t)generation << 1) | stream, 0x504F4E47u}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, out[4];
     eo_philox4x32(ctr, key, out);
     return out[0] & 1u;
 }
 
 /* -------------------------------------------------------- config.py:15-23, main.py:91-92 */
-void eo_action_to_input(const uint8_t action[16], a26o_input *in)
+/* gym-retro's button vector -> console input.  [3P-recall] 8 buttons per player (BUTTON, -, SELECT, RESET, UP, DOWN, LEFT,
+ * RIGHT); an env made with players=1 (main.py:40) consumes only action[0:8]; FILTERED cancels UP+DOWN / LEFT+RIGHT of one
+ * player.  What each button does to the console is a table (EO_BTN_*), by default the reference's own names: [0]
+ * RIGHT_PLAYER_START_BUTTON = fire of paddle 1, [15] LEFT_PLAYER_START_BUTTON = fire of paddle 0, [4]/[5] = right player
+ * (paddle 1) up/down, [6]/[7] = left player (paddle 0) up/down.  "up" (the reference's [1,0]) = lower resistance. */
+static uint8_t g_button_map[16] = {EO_BTN_FIRE_P0 + 1, 0, EO_BTN_SELECT, EO_BTN_RESET, EO_BTN_UP_P0 + 2, EO_BTN_UP_P0 + 3,
+                                   EO_BTN_UP_P0 + 0, EO_BTN_UP_P0 + 1, 0, 0, EO_BTN_SELECT, EO_BTN_RESET, 0, 0, 0, EO_BTN_FIRE_P0 + 0};
+void eo_set_button_map(const uint8_t map[16]) { memcpy(g_button_map, map, 16); }
+void eo_get_button_map(uint8_t map[16]) { memcpy(map, g_button_map, 16); }
+
+void eo_action_to_input(const uint8_t action[16], int players, a26o_input *in)
 {
-    in->swchb = 0x3F;
-    in->fire = (uint8_t)((action[15] ? 1 : 0) | (action[0] ? 2 : 0));   /* LEFT/RIGHT_PLAYER_START_BUTTON */
-    in->dec = in->inc = 0;
-    if (action[4] != action[5]) { if (action[4]) in->dec |= 2; else in->inc |= 2; }   /* right paddle = paddle 1 */
-    if (action[6] != action[7]) { if (action[6]) in->dec |= 1; else in->inc |= 1; }   /* left paddle  = paddle 0 */
+    in->swchb = 0x3F; in->fire = 0; in->dec = 0; in->inc = 0;
+    for (int p = 0; p < players && p < 2; ++p) {
+        const uint8_t *b = action + 8 * p;
+        const uint8_t *m = g_button_map + 8 * p;
+        int held[8];
+        for (int i = 0; i < 8; ++i) held[i] = b[i] != 0;
+        if (held[4] && held[5]) held[4] = held[5] = 0;      /* retro.Actions.FILTERED */
+        if (held[6] && held[7]) held[6] = held[7] = 0;
+        for (int i = 0; i < 8; ++i) {
+            if (!held[i]) continue;
+            int code = m[i];
+            if (code >= EO_BTN_FIRE_P0 && code < EO_BTN_FIRE_P0 + 4) in->fire |= (uint8_t)(1 << (code - EO_BTN_FIRE_P0));
+            else if (code >= EO_BTN_UP_P0 && code < EO_BTN_UP_P0 + 8) {
+                int paddle = (code - EO_BTN_UP_P0) / 2;
+                if ((code - EO_BTN_UP_P0) % 2) in->inc |= (uint8_t)(1 << paddle); else in->dec |= (uint8_t)(1 << paddle);
+            } else if (code == EO_BTN_SELECT) in->swchb &= (uint8_t)~0x02;
+            else if (code == EO_BTN_RESET) in->swchb &= (uint8_t)~0x01;
+        }
+    }
 }
 
 static void idle(a26o *env, uint8_t swchb, int frames)
@@ -175,23 +199,37 @@ static int hardcoded(const double x[6])
     return EO_ACT_NONE;
 }
 
+/* dumb_ais.py:1-8 (kind EO_POLICY_HARDCODED) and :11-25 (EO_POLICY_SCORE_HARDCODED, after set_score) */
+int eo_bot_act(int kind, const double x[6], int score1, int score2)
+{
+    if (kind == EO_POLICY_SCORE_HARDCODED && !(score1 <= score2)) return EO_ACT_NONE;
+    return hardcoded(x);
+}
+
+/* utils.py:139-153: the six-vector handed to model.run */
+void eo_inference_vector(const double ball[2], const double last[2], double me_row, double enemy_row, double x[6])
+{
+    x[0] = ball[1] / EO_GAME_WIDTH; x[1] = ball[0] / EO_PLAYABLE_HEIGHT; x[2] = last[1] / EO_GAME_WIDTH;
+    x[3] = last[0] / EO_PLAYABLE_HEIGHT; x[4] = me_row / EO_PLAYABLE_HEIGHT; x[5] = enemy_row / EO_PLAYABLE_HEIGHT;
+}
+
 /* utils.py:139-153 + model.run */
 static int inference(const eo_shape *sh, const double ball[2], const double last[2], double me_row, double enemy_row,
                      eo_policy pol, int score1, int score2)
 {
-    double x[6] = {ball[1] / EO_GAME_WIDTH, ball[0] / EO_PLAYABLE_HEIGHT, last[1] / EO_GAME_WIDTH,
-                   last[0] / EO_PLAYABLE_HEIGHT, me_row / EO_PLAYABLE_HEIGHT, enemy_row / EO_PLAYABLE_HEIGHT};
+    double x[6];
     int act;
+    eo_inference_vector(ball, last, me_row, enemy_row, x);
     switch (pol.kind) {
-    case EO_POLICY_HARDCODED: return hardcoded(x);
-    case EO_POLICY_SCORE_HARDCODED: return score1 <= score2 ? hardcoded(x) : EO_ACT_NONE;
+    case EO_POLICY_HARDCODED:
+    case EO_POLICY_SCORE_HARDCODED: return eo_bot_act(pol.kind, x, score1, score2);
     default: eo_mlp_forward(sh, pol.genome, x, NULL, &act); return act;
     }
 }
 
 /* ---------------------------------------------------------------- main.py:69-112 ------- */
 void eo_episode(a26o *env, const eo_shape *shape, eo_policy left, eo_policy right, double mult,
-                uint64_t seed, uint32_t env_id, int max_frames, eo_episode_result *res,
+                uint64_t seed, uint64_t generation, uint32_t env_id, int players, int max_frames, eo_episode_result *res,
                 uint8_t *trace, int trace_cap)
 {
     uint8_t action[16] = {0};
@@ -205,15 +243,15 @@ void eo_episode(a26o *env, const eo_shape *shape, eo_policy left, eo_policy righ
     int frame = 0, s1 = 0, s2 = 0;
     for (;;) {
         a26o_input in;
-        eo_action_to_input(action, &in);
+        eo_action_to_input(action, players, &in);
         a26o_run_frame(env, &in, fb);
         a26o_fb_to_rgb(fb, rgb);
         s1 = a26o_ram(env)[13]; s2 = a26o_ram(env)[14];
         eo_obs ob;
         eo_find_stuff(rgb, &ob);
         /* main.get_actions (main.py:138-154) */
-        int left_act = eo_philox_bit(seed, env_id, (uint32_t)frame, 0) ? EO_ACT_DOWN : EO_ACT_UP;
-        int right_act = eo_philox_bit(seed, env_id, (uint32_t)frame, 1) ? EO_ACT_DOWN : EO_ACT_UP;
+        int left_act = eo_philox_bit(seed, generation, env_id, (uint32_t)frame, 0) ? EO_ACT_DOWN : EO_ACT_UP;
+        int right_act = eo_philox_bit(seed, generation, env_id, (uint32_t)frame, 1) ? EO_ACT_DOWN : EO_ACT_UP;
         if (ob.valid[0]) {
             const double *ball = ob.loc[0];
             double lb[2] = {have_last_ball ? last_ball[0] : ball[0], have_last_ball ? last_ball[1] : ball[1]};
@@ -260,7 +298,7 @@ void eo_episode(a26o *env, const eo_shape *shape, eo_policy left, eo_policy righ
 /* ---------------------------------------------------------------- main.py:28-66 -------- */
 double eo_evaluate(const uint8_t rom[2048], const eo_shape *shape, const float *genome,
                    const float *hof_genomes, const double *hof_fitness, int n_hof, const int hof_pick[3],
-                   uint64_t seed, uint32_t genome_id, double rewards[EO_GAMES_TO_PLAY], int frames[EO_GAMES_TO_PLAY])
+                   uint64_t seed, uint64_t generation, uint32_t genome_id, double rewards[EO_GAMES_TO_PLAY], int frames[EO_GAMES_TO_PLAY])
 {
     a26o *env = a26o_new(rom);
     int G = eo_gene_size(shape);
@@ -281,7 +319,8 @@ double eo_evaluate(const uint8_t rom[2048], const eo_shape *shape, const float *
         }
         eo_reset_to_state(env, state);
         eo_episode_result r;
-        eo_episode(env, shape, left, right, mult, seed, genome_id * EO_GAMES_TO_PLAY + (uint32_t)i, 0, &r, NULL, 0);
+        eo_episode(env, shape, left, right, mult, seed, generation, genome_id * EO_GAMES_TO_PLAY + (uint32_t)i,
+                   state == EO_STATE_START_1P ? 1 : 2, 0, &r, NULL, 0);
         rewards[i] = r.reward; frames[i] = r.frames;
         sum += r.reward;
     }
@@ -290,11 +329,11 @@ double eo_evaluate(const uint8_t rom[2048], const eo_shape *shape, const float *
 }
 
 void eo_selfplay_game(const uint8_t rom[2048], const eo_shape *shape, const float *right, const float *left,
-                      uint64_t seed, uint32_t env_id, eo_episode_result *res)
+                      uint64_t seed, uint64_t generation, uint32_t env_id, eo_episode_result *res)
 {
     a26o *env = a26o_new(rom);
     eo_policy l = {EO_POLICY_MLP, left}, r = {EO_POLICY_MLP, right};
     eo_reset_to_state(env, EO_STATE_START_2P);
-    eo_episode(env, shape, l, r, 1.0, seed, env_id, 0, res, NULL, 0);
+    eo_episode(env, shape, l, r, 1.0, seed, generation, env_id, 2, 0, res, NULL, 0);
     a26o_free(env);
 }

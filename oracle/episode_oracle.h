@@ -68,11 +68,17 @@ void eo_mlp_forward(const eo_shape *, const float *genome, const double *x, doub
 void eo_find_stuff(const uint8_t *rgb /*[210][160][3]*/, eo_obs *out);
 int eo_clamp(int valid, double paddle_row, int action);
 double eo_reward(double mult, double total_frames, int my_score, int enemy_score);
-uint32_t eo_philox_bit(uint64_t seed, uint32_t env_id, uint32_t frame, uint32_t stream);
+int eo_bot_act(int kind, const double x[6], int score1, int score2);         /* dumb_ais.py:1-25 */
+void eo_inference_vector(const double ball[2], const double last[2], double me_row, double enemy_row, double x[6]);   /* utils.py:139-153 */
+uint32_t eo_philox_bit(uint64_t seed, uint64_t generation, uint32_t env_id, uint32_t frame, uint32_t stream);
 void eo_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
-/* retro action[16] -> console input (the reference-intent button map) */
-void eo_action_to_input(const uint8_t action[16], a26o_input *in);
+/* button map codes (one per gym-retro button; the product's NGP_BTN_* in include/ngp.h) */
+enum { EO_BTN_NONE = 0, EO_BTN_FIRE_P0 = 1, EO_BTN_UP_P0 = 5, EO_BTN_SELECT = 13, EO_BTN_RESET = 14 };
+void eo_set_button_map(const uint8_t map[16]);
+void eo_get_button_map(uint8_t map[16]);
+/* retro action[16] -> console input for an env made with `players` players (gym-retro button layout) */
+void eo_action_to_input(const uint8_t action[16], int players, a26o_input *in);
 /* power-on + scripted switches up to the reference's 'Start' / 'Start.2P' save states,
  * including gym-retro reset()'s one idle frame */
 void eo_reset_to_state(a26o *env, int state_id);
@@ -80,18 +86,18 @@ void eo_reset_to_state(a26o *env, int state_id);
 /* One perform_episode.  trace (optional) receives per frame 144 bytes:
  * RAM[128] | left_act right_act score1 score2 | valid[3] pad | timeout(u32) frame(u32) */
 void eo_episode(a26o *env, const eo_shape *shape, eo_policy left, eo_policy right, double mult,
-                uint64_t seed, uint32_t env_id, int max_frames, eo_episode_result *res,
+                uint64_t seed, uint64_t generation, uint32_t env_id, int players, int max_frames, eo_episode_result *res,
                 uint8_t *trace, int trace_cap);
 
 /* main.evaluate for one genome.  hof_pick[3]: HoF member index for games 3..5 (ignored when
  * n_hof == 0).  Returns the mean reward; rewards[6] and frames[6] are filled. */
 double eo_evaluate(const uint8_t rom[2048], const eo_shape *shape, const float *genome,
                    const float *hof_genomes, const double *hof_fitness, int n_hof, const int hof_pick[3],
-                   uint64_t seed, uint32_t genome_id, double rewards[EO_GAMES_TO_PLAY], int frames[EO_GAMES_TO_PLAY]);
+                   uint64_t seed, uint64_t generation, uint32_t genome_id, double rewards[EO_GAMES_TO_PLAY], int frames[EO_GAMES_TO_PLAY]);
 
 /* round-robin self-play game: right = genome a, left = genome b, 2-player start state */
 void eo_selfplay_game(const uint8_t rom[2048], const eo_shape *shape, const float *right, const float *left,
-                      uint64_t seed, uint32_t env_id, eo_episode_result *res);
+                      uint64_t seed, uint64_t generation, uint32_t env_id, eo_episode_result *res);
 
 #ifdef __cplusplus
 }

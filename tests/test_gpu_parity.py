@@ -60,12 +60,13 @@ def _oracle_trace(args):
 def test_env_step_trace_parity(engine, core):
     """core 0 = table-driven interpreter, core 1 = statically translated cartridge.  RAM, CPU registers, TIA digest (collision latches, positions, paddle charges), every frame
     (CRC of the RGB frame) and the fused find_stuff result, frame by frame, on random action traces
-    from both start states (BASELINE config 2's bit-exact RAM/frame check)."""
-    n_envs, n_frames = 16, 1200
+    from both start states (BASELINE config 2's bit-exact RAM/frame check: a 64-environment subset, more than 2 000 frames
+    each)."""
+    n_envs, n_frames = 64, 2100
     rng = np.random.RandomState(42)
     states = [i % 2 for i in range(n_envs)]
     acts = [_random_actions(rng, n_frames, hold=1 + 3 * (i % 5)) for i in range(n_envs)]
-    with cf.ProcessPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+    with cf.ProcessPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
         ref = list(ex.map(_oracle_trace, zip(states, acts)))
     for state in (0, 1):
         idx = [i for i in range(n_envs) if states[i] == state]
@@ -173,11 +174,11 @@ def test_evaluate_population_1024_properties(ngp):
     assert torch.equal(a["fitness"], b["fitness"]) and torch.equal(a["frames"], b["frames"])
     # CTA-synchronous launch geometry (what large populations use) gives the same bits
     for blk in ("128", "256"):
-        os.environ["NGP_ROLLOUT_BLOCK"] = blk
+        eng.set_option("rollout_block", int(blk))
         try:
             c = eng.evaluate(genomes, seed=1, want_detail=True)
         finally:
-            del os.environ["NGP_ROLLOUT_BLOCK"]
+            eng.set_option("rollout_block", 0)
         assert torch.equal(a["fitness"], c["fitness"]) and torch.equal(a["frames"], c["frames"]) and torch.equal(a["rewards"], c["rewards"])
     fit_h, total_h = eng.evaluate_host(genomes.cpu().numpy(), seed=1)
     assert np.array_equal(fit_h, a["fitness"].cpu().numpy()) and total_h == a["frames_total"]
@@ -334,11 +335,11 @@ def test_mlp_forward_tensor_core_path(ngp, nodes, envs):
     genomes = (rng.standard_normal((n, eng.gene_size)) * 0.08).astype(np.float32)
     x = rng.random_sample((n, envs, 6)).astype(np.float32)
     act, out = eng.mlp_forward(torch.from_numpy(genomes).cuda(), torch.from_numpy(x).cuda())
-    os.environ["NGP_MLP_NO_TF32"] = "1"
+    eng.set_option("mlp_no_tf32", 1)
     try:
         act_f, out_f = eng.mlp_forward(torch.from_numpy(genomes).cuda(), torch.from_numpy(x).cuda())
     finally:
-        del os.environ["NGP_MLP_NO_TF32"]
+        eng.set_option("mlp_no_tf32", 0)
     ref_out = np.zeros((n, envs, nodes[-1])); ref_act = np.zeros((n, envs), np.uint8)
     for g in range(n):
         for e in range(envs):

@@ -69,6 +69,21 @@ def test_reward_clamp_bots(golden):
             assert L.eo_clamp(0, float(y), act) == act
     sh = oracle.Shape.make([6, 2, 2])
     assert L.eo_gene_size(sh) == int(golden["gene_size_default"]) == 20
+    # dumb_ais.HardcodedAi / ScoreHardcodedAi on the reference's own outputs (32 vectors, 4 of them with ball_y == me_y;
+    # scores 0-1 = the bot acts, 2-1 = it stands still)
+    for x, hb, sb in zip(golden["bots_x"], golden["bots_hard"], golden["bots_score"]):
+        assert oracle.bot_act(oracle.POLICY_HARDCODED, x) == hb
+        assert oracle.bot_act(oracle.POLICY_SCORE_HARDCODED, x, 0, 1) == sb[0]
+        assert oracle.bot_act(oracle.POLICY_SCORE_HARDCODED, x, 2, 1) == sb[1]
+    assert set(golden["bots_hard"].tolist()) == {0, 1, 2} and set(golden["bots_score"][:, 1].tolist()) == {0}
+
+
+def test_inference_vector_matches_reference(golden, obs_npy):
+    """utils.inference's six-vector for the right player on obs.npy (last ball = ball), bit-exact float64."""
+    loc, valid = oracle.find_stuff(obs_npy)
+    x = oracle.inference_vector(loc[0], loc[0], loc[2][0], loc[1][0])
+    assert np.array_equal(x, golden["inference_right_on_obs"])
+    assert x.tolist() == [0.403125, 0.696875, 0.403125, 0.696875, 0.796875, 0.765625]      # SURVEY Appendix D
 
 
 def test_philox_known_answer():

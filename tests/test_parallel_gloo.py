@@ -1,8 +1,12 @@
-"""World-size-2 gloo tests of the multi-GPU host logic (sharding, fitness all-gather, elite merge)."""
+"""World-size-2 and -3 gloo tests of the multi-GPU host logic: sharding (even and uneven), elite quotas and the
+all-gather of the fixed-size per-rank records.  The records themselves are packed / unpacked by CUDA kernels in the product
+(ngp_pack_elites / ngp_unpack_elites, covered by the -m gpu tests); here the numpy restatement of the record layout in
+oracle/ stands in for them, so that the collective plumbing (parallel.gather_records) runs on CPU tensors over gloo."""
 import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -14,16 +18,25 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, q):
+def _population(n_total, G):
+    rng = np.random.RandomState(0)
+    return np.round(rng.standard_normal(n_total), 1), rng.random_sample((n_total, G)).astype(np.float32)
+
+
+def _worker(rank, world, port, n_total, k_total, q):
+    import oracle
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    n_total, G, k = 10, 5, 2
-    rng = np.random.RandomState(0)
-    fitness_all = torch.from_numpy(np.round(rng.standard_normal(n_total), 1))
-    genomes_all = torch.from_numpy(rng.random_sample((n_total, G)).astype(np.float32))
+    G = 5
+    fitness_all, genomes_all = _population(n_total, G)
     lo, hi = parallel.shard_bounds(n_total, world, rank)
-    gf, eg, ef = parallel.exchange_generation(fitness_all[lo:hi].clone(), genomes_all[lo:hi].clone(), k)
-    q.put((rank, gf.numpy(), eg.numpy(), ef.numpy()))
+    sizes = parallel.shard_sizes(n_total, world); counts = parallel.elite_counts(n_total, world, k_total)
+    n_max, k_max = max(sizes), max(counts)
+    rec = oracle.pack_record(genomes_all[lo:hi], fitness_all[lo:hi], counts[rank], n_max, k_max)
+    gathered, work = parallel.gather_records(torch.from_numpy(rec), async_op=True)
+    work.wait()
+    fit, eg, ef = oracle.unpack_records(gathered.numpy(), world, n_max, k_max, G)
+    q.put((rank, fit, eg, ef))
     dist.destroy_process_group()
 
 
@@ -35,37 +48,34 @@ def test_shard_bounds_cover_population():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+            assert sizes == parallel.shard_sizes(n, w)
+            counts = parallel.elite_counts(n, w, n // 4)
+            assert all(0 <= c <= s for c, s in zip(counts, sizes))
 
 
-def test_exchange_generation_world2():
-    world, port = 2, _free_port()
+@pytest.mark.parametrize("world,n_total,k_total", [(2, 10, 4), (3, 10, 4), (3, 11, 9)])
+def test_record_allgather(world, n_total, k_total):
+    """Every rank ends with the same global fitness vector (rank order = population order) and the same merged elites (each
+    shard's best first), also when the shards differ in size (10 genomes on 3 ranks)."""
+    port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, k_total, q)) for r in range(world)]
     [p.start() for p in procs]
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
     [p.join(timeout=60) for p in procs]
-    rng = np.random.RandomState(0)
-    fitness_all = np.round(rng.standard_normal(10), 1)
-    genomes_all = rng.random_sample((10, 5)).astype(np.float32)
-    # every rank sees the same global fitness and the same merged elites
-    for rank, gf, eg, ef in res:
-        assert np.array_equal(gf, fitness_all)
-        assert np.array_equal(eg, res[0][2]) and np.array_equal(ef, res[0][3])
-    # elites = top-2 of each shard, merged best-first
+    fitness_all, genomes_all = _population(n_total, 5)
+    counts = parallel.elite_counts(n_total, world, k_total)
     expect = []
-    for r in range(2):
-        lo, hi = parallel.shard_bounds(10, 2, r)
-        order = np.argsort(-fitness_all[lo:hi], kind="stable")[:2] + lo
-        expect += list(order)
-    expect = sorted(expect, key=lambda i: -fitness_all[i])
-    assert np.array_equal(res[0][3], fitness_all[expect])
-    assert np.array_equal(res[0][2], genomes_all[expect])
+    for r in range(world):
+        lo, hi = parallel.shard_bounds(n_total, world, r)
+        expect += list(np.argsort(-fitness_all[lo:hi], kind="stable")[:counts[r]] + lo)
+    for rank, fit, eg, ef in res:
+        assert np.array_equal(fit, fitness_all)
+        assert np.array_equal(ef, fitness_all[expect]) and np.array_equal(eg, genomes_all[expect])
 
 
-def test_exchange_generation_single_process():
-    f = torch.tensor([0.1, 0.9, 0.5], dtype=torch.float64)
-    g = torch.arange(6, dtype=torch.float32).reshape(3, 2)
-    gf, eg, ef = parallel.exchange_generation(f, g, 2)
-    assert torch.equal(gf, f) and ef.tolist() == [0.9, 0.5] and eg.tolist() == [[2.0, 3.0], [4.0, 5.0]]
-    assert parallel.global_stats(f)[2:] == (0.1, 0.9)
+def test_gather_records_without_process_group():
+    rec = torch.arange(32, dtype=torch.uint8)
+    gathered, work = parallel.gather_records(rec)
+    assert work is None and torch.equal(gathered, rec)
