@@ -44,6 +44,9 @@ static inline int __syncthreads_or(int v) { return v; }
 #include "../../neuro_genetic_pong_self_play_b200/csrc/host_tables.h"
 
 namespace {
+// ngp_default_config's button map (csrc/ngp_core.cu)
+const uint8_t kDefaultButtonMap[16] = {NGP_BTN_FIRE_P0 + 1, 0, NGP_BTN_SELECT, NGP_BTN_RESET, NGP_BTN_UP_P0 + 2, NGP_BTN_UP_P0 + 3,
+                                       NGP_BTN_UP_P0 + 0, NGP_BTN_UP_P0 + 1, 0, 0, NGP_BTN_SELECT, NGP_BTN_RESET, 0, 0, 0, NGP_BTN_FIRE_P0 + 0};
 // same palette the product uploads (csrc/ngp_core.cu: ngp_ntsc_palette)
 const uint32_t kPalette[128] = {
     0x000000, 0x4a4a4a, 0x6f6f6f, 0x8e8e8e, 0xaaaaaa, 0xc0c0c0, 0xd6d6d6, 0xececec, 0x484800, 0x69690f, 0x86861d, 0xa2a22a,
@@ -67,6 +70,7 @@ struct Sim {
     a26::Chip s;
     a26::CpuRegs r;
     uint32_t ram_words[32 * 32];   // lane 0 of a warp-interleaved block
+    int players = 2;               // the robot game ('Start') is made with players=1 (main.py:40)
 };
 }  // namespace
 
@@ -92,11 +96,13 @@ void hs_env_reset(void *h, int state)
 {
     Sim *sim = (Sim *)h;
     roll::load_snapshot(&sim->start[state], sim->s, sim->r, a26::Ram{sim->ram_words});
+    sim->players = state == NGP_STATE_START_1P ? 1 : 2;
 }
 void hs_env_power_on(void *h)
 {
     Sim *sim = (Sim *)h;
     a26::power_on(sim->s, sim->r, sim->T, a26::Ram{sim->ram_words}, sim->needed.data());
+    sim->players = 2;
 }
 
 // raw console input step (like a26o_run_frame)
@@ -142,9 +148,8 @@ int hs_env_step_fast(void *h, int core, const uint8_t *action16, uint8_t *ram_ou
     Sim *sim = (Sim *)h;
     a26::Ram ram{sim->ram_words};
     a26::Chip &s = sim->s;
-    uint32_t fire, dec, inc;
-    roll::action_to_input(action16, fire, dec, inc);
-    a26::apply_input(s, sim->needed.data(), 0x3F, fire, dec, inc);
+    const uint32_t in = roll::action_to_input(action16, sim->players, kDefaultButtonMap);
+    a26::apply_input(s, sim->needed.data(), in & 0xFF, (in >> 8) & 15, (in >> 12) & 15, (in >> 16) & 15);
     a26::clear_obs(s);
     if (core) a26::run_frame_compiled<false, false>(s, sim->r, sim->T, ram, nullptr);
     else a26::run_frame<false>(s, sim->r, sim->T, ram, nullptr);
@@ -159,9 +164,8 @@ int hs_env_step_fast(void *h, int core, const uint8_t *action16, uint8_t *ram_ou
 
 int hs_env_step(void *h, int core, const uint8_t *action16, uint8_t *ram_out, uint8_t *fb, double *loc, uint8_t *valid, uint8_t *regs, uint32_t *digest)
 {
-    uint32_t fire, dec, inc;
-    roll::action_to_input(action16, fire, dec, inc);
-    return hs_env_run_frame(h, core, 0x3F, (int)fire, (int)dec, (int)inc, ram_out, fb, loc, valid, regs, digest);
+    const uint32_t in = roll::action_to_input(action16, ((Sim *)h)->players, kDefaultButtonMap);
+    return hs_env_run_frame(h, core, in & 0xFF, (int)((in >> 8) & 15), (int)((in >> 12) & 15), (int)((in >> 16) & 15), ram_out, fb, loc, valid, regs, digest);
 }
 
 // fused evaluation, lanes executed one after another
@@ -182,6 +186,15 @@ void hs_evaluate(void *h, int core, const int32_t *nodes, int n_layers, int bias
     for (int i = 0; i + 1 < n_layers; ++i) G += (nodes[i] + (bias ? 1 : 0)) * nodes[i + 1];
     p.G = G;
     p.rewards = rewards; p.frames = frames;
+    for (int players = 1; players <= 2; ++players)                 // as ngp_evaluate builds it (csrc/ngp_core.cu)
+        for (int la = 0; la < 3; ++la)
+            for (int ra = 0; ra < 3; ++ra) {
+                uint8_t a[16] = {0};
+                a[0] = 1; a[15] = 1;
+                a[4] = ra == pol::ACT_UP; a[5] = ra == pol::ACT_DOWN;
+                a[6] = la == pol::ACT_UP; a[7] = la == pol::ACT_DOWN;
+                p.input_table[players - 1][la * 3 + ra] = roll::action_to_input(a, players, kDefaultButtonMap);
+            }
     a26::Ram ram{sim->ram_words};
     for (int e = 0; e < n * games; ++e) {
         roll::Episode ep;
