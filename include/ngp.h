@@ -200,7 +200,7 @@ int ngp_unpack_elites(ngp_handle *h, const void *gathered, int32_t world, int32_
                       float *elite_genomes, double *elite_fitness, void *stream);
 
 /* Tuning switches (experiments, geometry-independence tests): "rollout_block" (threads per CTA), "rollout_nosync",
- * "rollout_flavour" (1..3), "rollout_blocks_per_sm", "mlp_no_tf32".  value 0 restores the automatic choice. */
+ * "rollout_flavour" (1..3), "rollout_blocks_per_sm", "rollout_nocompact" (one launch, no tail compaction), "mlp_no_tf32".  value 0 restores the automatic choice. */
 int ngp_set_option(ngp_handle *h, const char *name, int64_t value);
 
 /* Device-side timing of the dominant kernel (the fused rollout) with CUDA events recorded on the

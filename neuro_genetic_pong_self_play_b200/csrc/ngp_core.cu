@@ -192,7 +192,34 @@ __global__ void __launch_bounds__(MAXT, 1) rollout_kernel(RolloutParams p)
     ep.env = -1;
     bool exhausted = false;
     unsigned long long my_frames = 0;
+    if (p.resume) {                     // second launch of a compacted evaluation: continue a parked environment
+        const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+        if (idx < (unsigned)p.counters[4]) {
+            const roll::Parked *pk = p.parked + idx;
+            ep = pk->ep;
+            load_snapshot(&pk->snap, s, r, ram);
+        }
+    }
     for (;;) {
+        if (p.suspend_below) {
+            // every lane sees the same answer eventually: the count of unfinished episodes only falls
+            bool park = false;
+            if (SYNC) {
+                if (threadIdx.x == 0) park = (long long)total - (long long)*(volatile unsigned long long *)&p.counters[3] < p.suspend_below;
+                park = __syncthreads_or(park);
+            } else {
+                if (lane == 0) park = (long long)total - (long long)*(volatile unsigned long long *)&p.counters[3] < p.suspend_below;
+                park = __shfl_sync(0xFFFFFFFFu, park, 0);
+            }
+            if (park) {
+                if (ep.env >= 0) {
+                    roll::Parked *pk = p.parked + atomicAdd(&p.counters[4], 1ull);
+                    pk->ep = ep;
+                    store_snapshot(&pk->snap, s, r, ram);
+                }
+                break;
+            }
+        }
         if (ep.env < 0 && !exhausted) {
             int e = (int)atomicAdd(&p.counters[0], 1ull);
             if (e < total) roll::episode_begin(ep, p, e, s, r, ram);
@@ -210,6 +237,7 @@ __global__ void __launch_bounds__(MAXT, 1) rollout_kernel(RolloutParams p)
                 p.rewards[ep.env] = reward;
                 p.frames[ep.env] = ep.frame;
                 if (s.error) atomicAdd(&p.counters[2], 1ull);
+                if (p.suspend_below) atomicAdd(&p.counters[3], 1ull);
                 ep.env = -1;
             }
         }
@@ -218,6 +246,8 @@ __global__ void __launch_bounds__(MAXT, 1) rollout_kernel(RolloutParams p)
     for (int off = 16; off; off >>= 1) my_frames += __shfl_down_sync(0xFFFFFFFFu, my_frames, off);
     if (lane == 0 && my_frames) atomicAdd(&p.counters[1], my_frames);
 }
+
+int ngp_evaluate_stepwise(ngp_handle *h, const RolloutParams &p, cudaStream_t st);     // ngp_stepwise.cu
 
 // fitness[g] = sum(rewards[g][:]) / games, summed in game order (main.py:65)
 __global__ void fitness_reduce_kernel(const double *__restrict__ rewards, int n, int games, double *__restrict__ fitness)
@@ -263,6 +293,7 @@ extern "C" int ngp_set_option(ngp_handle *h, const char *name, int64_t value)
     else if (n == "rollout_flavour") h->opt_rollout_lean = (int)value;
     else if (n == "rollout_blocks_per_sm") h->opt_rollout_blocks_per_sm = (int)value;
     else if (n == "mlp_no_tf32") h->opt_mlp_no_tf32 = value != 0;
+    else if (n == "rollout_nocompact") h->opt_rollout_nocompact = value != 0;
     else { ngp_set_error("ngp_set_option: unknown option '%s'", name); return NGP_ERR_INVALID; }
     return NGP_OK;
 }
@@ -299,9 +330,9 @@ extern "C" int ngp_create(const ngp_config *cfg, const uint8_t *rom, int32_t dev
     NGP_CUDA(cudaMalloc(&h->d_palette, sizeof(ngp_ntsc_palette)));
     NGP_CUDA(cudaMemcpy(h->d_palette, ngp_ntsc_palette, sizeof(ngp_ntsc_palette), cudaMemcpyHostToDevice));
     NGP_CUDA(cudaMalloc(&h->d_start, 2 * sizeof(Snapshot)));
-    NGP_CUDA(cudaMalloc(&h->d_counters, 4 * sizeof(unsigned long long)));
-    NGP_CUDA(cudaMemset(h->d_counters, 0, 4 * sizeof(unsigned long long)));
-    NGP_CUDA(cudaMallocHost(&h->h_counters, 4 * sizeof(unsigned long long)));
+    NGP_CUDA(cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long)));
+    NGP_CUDA(cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned long long)));
+    NGP_CUDA(cudaMallocHost(&h->h_counters, 8 * sizeof(unsigned long long)));
     // The two start snapshots depend on the cartridge image only: built once per process by the CUDA core (a single warp,
     // tens of milliseconds) and kept as an immutable host copy for later handles.
     {
@@ -332,6 +363,8 @@ extern "C" int ngp_destroy(ngp_handle *h)
     cudaFree(h->d_envs); cudaFree(h->d_fb); cudaFree(h->d_rewards); cudaFree(h->d_frames); cudaFree(h->d_counters);
     cudaFree(h->d_genomes_stage); cudaFree(h->d_fitness_stage); cudaFree(h->d_hof_stage); cudaFree(h->d_hof_fit_stage);
     cudaFree(h->mlp_a); cudaFree(h->mlp_b); cudaFree(h->mlp_z); cudaFree(h->d_parent);
+    cudaFree(h->d_parked);
+    cudaFree(h->step_envs); cudaFree(h->step_x); cudaFree(h->step_act); cudaFree(h->step_opp);
     cudaFree(h->hof_hash_old); cudaFree(h->hof_hash_new); cudaFree(h->hof_order); cudaFree(h->hof_tmp_genomes); cudaFree(h->hof_tmp_fitness);
     cudaFreeHost(h->h_genomes); cudaFreeHost(h->h_fitness); cudaFreeHost(h->h_counters);
     if (h->prof_events) { for (auto &e : *h->prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } delete h->prof_events; }
@@ -416,12 +449,10 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
 {
     NGP_REQUIRE(h && genomes && fitness && n > 0, "ngp_evaluate: bad arguments");
     NGP_REQUIRE(n_hof == 0 || (hof_genomes && hof_fitness), "ngp_evaluate: hall of fame pointers missing");
-    for (int i = 0; i < h->cfg.n_layers; ++i)
-        if (h->cfg.nodes[i] > pol::FUSED_MAX_WIDTH) {
-            ngp_set_error("ngp_evaluate: layer width %d exceeds the fused rollout's limit %d; use ngp_env_step + ngp_mlp_forward",
-                          h->cfg.nodes[i], pol::FUSED_MAX_WIDTH);
-            return NGP_ERR_UNSUPPORTED;
-        }
+    bool wide = false;            // a layer too wide for the fused thread-per-environment MLP: per-frame stepwise driver (ngp_stepwise.cu)
+    for (int i = 0; i < h->cfg.n_layers; ++i) wide |= h->cfg.nodes[i] > pol::FUSED_MAX_WIDTH;
+    NGP_REQUIRE(!wide || (h->cfg.nodes[0] == 6 && h->cfg.nodes[h->cfg.n_layers - 1] <= 8),
+                "ngp_evaluate: wide networks need 6 inputs and at most 8 outputs");
     if (h->cfg.schedule == NGP_SCHEDULE_REFERENCE)
         NGP_REQUIRE(h->cfg.games_to_play <= NGP_GAMES_TO_PLAY, "ngp_evaluate: the reference schedule has at most 6 games");
     NGP_CUDA(cudaSetDevice(h->device));
@@ -436,7 +467,7 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
         NGP_CUDA(cudaMalloc(&h->d_frames, (size_t)total * sizeof(int32_t)));
         h->cap_eval = (int)total;
     }
-    NGP_CUDA(cudaMemsetAsync(h->d_counters, 0, 4 * sizeof(unsigned long long), st));
+    NGP_CUDA(cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), st));
     RolloutParams p;
     p.tables = h->d_tables; p.needed = h->d_needed; p.start = h->d_start;
     p.genomes = genomes; p.hof_genomes = hof_genomes; p.hof_fitness = hof_fitness; p.hof_pick = hof_pick;
@@ -459,6 +490,19 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
                 p.input_table[players - 1][la * 3 + ra] = roll::action_to_input(a, players, h->cfg.button_map);
             }
     p.rewards = rewards ? rewards : h->d_rewards; p.frames = frames ? frames : h->d_frames; p.counters = h->d_counters;
+    if (wide) {
+        const int rc = ngp_evaluate_stepwise(h, p, st);
+        if (rc != NGP_OK) return rc;
+        fitness_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(p.rewards, n, games, fitness);
+        h->launches++;
+        NGP_CUDA(cudaGetLastError());
+        if (frames_total) *frames_total = h->h_counters[1];
+        if (h->h_counters[2]) {
+            ngp_set_error("ngp_evaluate: %llu environments stopped on an emulator error", h->h_counters[2]);
+            return NGP_ERR_EMULATOR;
+        }
+        return NGP_OK;
+    }
     // Launch geometry (measured, profiles/README.md).  Small launches: one-warp CTAs spread over all SMs.  From ~2 warps per
     // SM upwards the CTA-synchronous flavour wins: all warps of a CTA walk through the frame together and share their
     // instruction fetches; the CTA grows with the launch until one 16-warp CTA per SM (128 registers/thread) is reached.
@@ -509,9 +553,33 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
         h->prof_used++;
         NGP_CUDA(cudaEventRecord(ev0, st));
     }
+    // Tail compaction.  A generation lasts as long as its longest episode; once the queue is empty the resident warps thin out
+    // to a few live lanes each but keep sharing their schedulers.  When the launch holds more environments than one dense warp
+    // per scheduler can take (sm_count * 4 * 32), the first launch parks every unfinished environment as soon as fewer than
+    // that many are left, and a second launch of one-warp CTAs (full register budget) finishes them at single-warp latency.
+    const long long dense = (long long)h->sm_count * 4 * 32;
+    const bool compact = p.core && sync && total > 2 * dense && !h->opt_rollout_nocompact;
+    p.suspend_below = compact ? (int)dense : 0;
+    p.resume = 0;
+    p.parked = nullptr;
+    if (compact) {
+        const size_t need = (size_t)dense * sizeof(roll::Parked);
+        if (need > h->cap_parked) {
+            cudaFree(h->d_parked); h->d_parked = nullptr; h->cap_parked = 0;
+            NGP_CUDA(cudaMalloc(&h->d_parked, need));
+            h->cap_parked = need;
+        }
+        p.parked = (roll::Parked *)h->d_parked;
+    }
     kernel<<<(unsigned)blocks, block, smem, st>>>(p);
     h->launches++;
     NGP_CUDA(cudaGetLastError());
+    if (compact) {
+        p.suspend_below = 0; p.resume = 1;
+        rollout_kernel<1, false, 256><<<(unsigned)(dense / 32), 32, 32 * 32 * 4, st>>>(p);
+        h->launches++;
+        NGP_CUDA(cudaGetLastError());
+    }
     if (ev1) NGP_CUDA(cudaEventRecord(ev1, st));
     fitness_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(p.rewards, n, games, fitness);
     h->launches++;

@@ -33,6 +33,7 @@ struct ngp_handle {
     int32_t *d_frames;            // [cap_eval]
     unsigned long long *d_counters;   // [0] next env, [1] frames, [2] emulator errors
     int cap_eval;
+    void *d_parked; size_t cap_parked;    // environments parked between the two launches of a compacted evaluation (roll::Parked)
     // host staging (pinned) for the *_host entry points
     float *h_genomes; double *h_fitness; float *d_genomes_stage; double *d_fitness_stage;
     size_t stage_genomes, stage_fitness;
@@ -44,10 +45,14 @@ struct ngp_handle {
     int32_t *d_parent; size_t cap_parent;                                   // ngp_ga_step selection winners
     uint64_t *hof_hash_old, *hof_hash_new; int32_t *hof_order; float *hof_tmp_genomes; double *hof_tmp_fitness;   // ngp_hof_update
     size_t hof_cap_hash_old, hof_cap_hash_new, hof_cap_order, hof_cap_tmp_genomes, hof_cap_tmp_fitness;
+    // ngp_evaluate for nets wider than the fused rollout (ngp_stepwise.cu): per-environment state, MLP input rows, actions,
+    // gathered hall-of-fame opponents
+    void *step_envs; float *step_x; uint8_t *step_act; float *step_opp;
+    size_t step_cap_envs, step_cap_x, step_cap_act, step_cap_opp;
     int fs_per_sm;                                                          // resident find_stuff CTAs per SM
     int tf32_attr_set;                                                      // dynamic shared memory opt-in done
     // ngp_set_option (tuning experiments; 0 = automatic)
-    int opt_rollout_block, opt_rollout_nosync, opt_rollout_lean, opt_rollout_blocks_per_sm, opt_mlp_no_tf32;
+    int opt_rollout_block, opt_rollout_nosync, opt_rollout_lean, opt_rollout_blocks_per_sm, opt_mlp_no_tf32, opt_rollout_nocompact;
     // profiling of the rollout kernel
     int profile_on;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *prof_events;
