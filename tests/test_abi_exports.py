@@ -70,3 +70,32 @@ def test_generated_core_is_up_to_date(tmp_path):
     subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_rom_core.py"), str(out)])
     committed = open(os.path.join(ROOT, "neuro_genetic_pong_self_play_b200", "csrc", "generated", "pong_core.inc")).read()
     assert out.read_text() == committed
+
+
+def test_integration_md_struct_matches_header():
+    """The ctypes struct INTEGRATION.md tells a maintainer to paste must be the library's ngp_config field for field."""
+    import ctypes
+    import re
+    from neuro_genetic_pong_self_play_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class NgpConfig\(ctypes\.Structure\):.*?\n    _fields_ = \[(.*?)\]\n", text, re.S)
+    assert m, "INTEGRATION.md lost its NgpConfig definition"
+    ns = {"ctypes": ctypes}
+    exec("class NgpConfig(ctypes.Structure):\n    _fields_ = [" + m.group(1) + "]\n", ns)
+    doc, real = ns["NgpConfig"], _lib.NgpConfig
+    assert [f[0] for f in doc._fields_] == [f[0] for f in real._fields_]
+    assert ctypes.sizeof(doc) == ctypes.sizeof(real)
+    for (name, _), (_, _) in zip(doc._fields_, real._fields_):
+        assert getattr(doc, name).offset == getattr(real, name).offset and getattr(doc, name).size == getattr(real, name).size, name
+    # and the header itself: every field name of the binding appears, in order, in include/ngp.h's struct
+    hdr = open(os.path.join(ROOT, "include", "ngp.h")).read()
+    body = hdr[hdr.index("typedef struct {"):hdr.index("} ngp_config;")]
+    pos = -1
+    for name, _ in real._fields_:
+        nxt = body.find(name, pos + 1)
+        assert nxt > pos, f"{name} missing or out of order in include/ngp.h"
+        pos = nxt
+    if os.path.exists(_lib.lib_path()):
+        L = ctypes.CDLL(_lib.lib_path())
+        L.ngp_config_size.restype = ctypes.c_int32
+        assert L.ngp_config_size() == ctypes.sizeof(doc)
