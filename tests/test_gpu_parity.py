@@ -418,3 +418,21 @@ def test_tail_compaction_gives_the_same_bits(ngp):
     assert a["frames_total"] == c["frames_total"] == int(a["frames"].sum().item())
     assert a["frames"].max().item() > 2 * a["frames"].float().mean().item()      # there is a tail to compact
     eng.close()
+
+
+@pytest.mark.parametrize("core", [0, 1])
+def test_cuda_core_reproduces_obs_npy_pixel_for_pixel(engine, obs_npy, core):
+    """The committed button trace (tests/golden/obs_trace.npz) through ngp_env_step: the frame equals the reference's real
+    gym-retro frame obs.npy byte for byte, and the fused find_stuff result is the reference's."""
+    tr = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "obs_trace.npz"))
+    engine.env_reset(2, int(tr["state"]))
+    for a in tr["actions"][:-1]:
+        engine.env_step(torch.from_numpy(np.stack([a, a])).cuda(), want_frames=False, want_obs=False, core=core)
+    a = tr["actions"][-1]
+    out = engine.env_step(torch.from_numpy(np.stack([a, a])).cuda(), core=core)
+    for j in range(2):
+        assert np.array_equal(out["frames"][j].cpu().numpy(), obs_npy)
+    assert out["valid"][0].cpu().tolist() == [1, 1, 1]
+    assert out["loc"][0].cpu().tolist() == [[111.5, 64.5], [122.5, 17.5], [127.5, 141.5]]
+    loc, valid = engine.find_stuff(out["frames"])
+    assert torch.equal(loc[0], out["loc"][0]) and valid[0].cpu().tolist() == [1, 1, 1]

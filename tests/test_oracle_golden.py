@@ -2,6 +2,7 @@
 from the imported reference code) and against obs.npy, the only emulator-side fixture the
 reference ships."""
 import hashlib
+import os
 
 import numpy as np
 
@@ -135,3 +136,18 @@ def test_episode_bots_play_to_win_score():
     sc = trace[:, 130:132].astype(int)
     assert np.all(np.diff(sc, axis=0) >= 0)
     assert res.reward == oracle.lib().eo_reward(1.0, res.total_frames, res.score2, res.score1)
+
+
+def test_emulator_reproduces_obs_npy_pixel_for_pixel(obs_npy):
+    """tests/golden/obs_trace.npz (found by tools/search_obs_trace.py): 353 env.step calls from 'Start.2P' after which the
+    emulated frame equals the reference's real gym-retro frame obs.npy in every one of its 210 x 160 x 3 bytes -- rendering,
+    colours, score digits, and ball / paddle positions reachable by the emulated game's own dynamics."""
+    tr = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "obs_trace.npz"))
+    env = oracle.Atari()
+    env.reset_to_state(int(tr["state"]))
+    for a in tr["actions"]:
+        fb = env.step(a)
+    assert np.array_equal(oracle.fb_to_rgb(fb), obs_npy)
+    assert env.ram[13] == 0 and env.ram[14] == 0
+    loc, valid = oracle.find_stuff(oracle.fb_to_rgb(fb))
+    assert valid.tolist() == [1, 1, 1] and loc.tolist() == [[111.5, 64.5], [122.5, 17.5], [127.5, 141.5]]       # SURVEY Appendix D
