@@ -162,7 +162,10 @@ int ngp_init_population(ngp_handle *h, float *genomes, int32_t n, uint64_t seed,
 /* toolbox.select / toolbox.mate / toolbox.mutate as separate callables (ga.py:89-94), the same arithmetic and the same
  * Philox streams as ngp_ga_step.
  * ngp_select: DEAP selTournament(individuals, k, tournsize = cfg.tournament_size): fitness f64[n] -> parent_idx i32[k];
- *   draws: optional device i32[k][tournsize] aspirant indices (NULL = Philox(seed, generation)).
+ *   draws: optional device i32[k][tournsize] aspirant indices (NULL = Philox(seed, generation)).  Without injected draws
+ *   and from 8192 aspirants per tournament upwards the winners are drawn from the tournament's order statistics on the
+ *   fitness-sorted population (one uniform per slot, ties uniform inside the tie group): the same distribution as
+ *   tournsize draws per slot, in O(N log^2 N) instead of O(N * tournsize).
  * ngp_mate: DEAP cxBlend(ind1, ind2, cfg.cx_alpha) in place on two device genomes f32[G]; u: optional device f32[G]
  *   uniforms (NULL = the Philox stream of pair `pair`).
  * ngp_mutate: DEAP mutGaussian(ind, mu, sigma, indpb) in place; u / z: optional device f32[G] uniforms / standard normals
@@ -200,7 +203,8 @@ int ngp_unpack_elites(ngp_handle *h, const void *gathered, int32_t world, int32_
                       float *elite_genomes, double *elite_fitness, void *stream);
 
 /* Tuning switches (experiments, geometry-independence tests): "rollout_block" (threads per CTA), "rollout_nosync",
- * "rollout_flavour" (1..3), "rollout_blocks_per_sm", "rollout_nocompact" (one launch, no tail compaction), "mlp_no_tf32".  value 0 restores the automatic choice. */
+ * "rollout_flavour" (1..3), "rollout_blocks_per_sm", "mlp_no_tf32", "select_os_min_t" (smallest tournament size that uses the
+ * order-statistics selection, default 8192).  value 0 restores the automatic choice. */
 int ngp_set_option(ngp_handle *h, const char *name, int64_t value);
 
 /* Device-side timing of the dominant kernel (the fused rollout) with CUDA events recorded on the

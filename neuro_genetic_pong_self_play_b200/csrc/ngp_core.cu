@@ -192,34 +192,7 @@ __global__ void __launch_bounds__(MAXT, 1) rollout_kernel(RolloutParams p)
     ep.env = -1;
     bool exhausted = false;
     unsigned long long my_frames = 0;
-    if (p.resume) {                     // second launch of a compacted evaluation: continue a parked environment
-        const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-        if (idx < (unsigned)p.counters[4]) {
-            const roll::Parked *pk = p.parked + idx;
-            ep = pk->ep;
-            load_snapshot(&pk->snap, s, r, ram);
-        }
-    }
     for (;;) {
-        if (p.suspend_below) {
-            // every lane sees the same answer eventually: the count of unfinished episodes only falls
-            bool park = false;
-            if (SYNC) {
-                if (threadIdx.x == 0) park = (long long)total - (long long)*(volatile unsigned long long *)&p.counters[3] < p.suspend_below;
-                park = __syncthreads_or(park);
-            } else {
-                if (lane == 0) park = (long long)total - (long long)*(volatile unsigned long long *)&p.counters[3] < p.suspend_below;
-                park = __shfl_sync(0xFFFFFFFFu, park, 0);
-            }
-            if (park) {
-                if (ep.env >= 0) {
-                    roll::Parked *pk = p.parked + atomicAdd(&p.counters[4], 1ull);
-                    pk->ep = ep;
-                    store_snapshot(&pk->snap, s, r, ram);
-                }
-                break;
-            }
-        }
         if (ep.env < 0 && !exhausted) {
             int e = (int)atomicAdd(&p.counters[0], 1ull);
             if (e < total) roll::episode_begin(ep, p, e, s, r, ram);
@@ -237,7 +210,6 @@ __global__ void __launch_bounds__(MAXT, 1) rollout_kernel(RolloutParams p)
                 p.rewards[ep.env] = reward;
                 p.frames[ep.env] = ep.frame;
                 if (s.error) atomicAdd(&p.counters[2], 1ull);
-                if (p.suspend_below) atomicAdd(&p.counters[3], 1ull);
                 ep.env = -1;
             }
         }
@@ -293,7 +265,7 @@ extern "C" int ngp_set_option(ngp_handle *h, const char *name, int64_t value)
     else if (n == "rollout_flavour") h->opt_rollout_lean = (int)value;
     else if (n == "rollout_blocks_per_sm") h->opt_rollout_blocks_per_sm = (int)value;
     else if (n == "mlp_no_tf32") h->opt_mlp_no_tf32 = value != 0;
-    else if (n == "rollout_nocompact") h->opt_rollout_nocompact = value != 0;
+    else if (n == "select_os_min_t") h->opt_select_os_min_t = (int)value;
     else { ngp_set_error("ngp_set_option: unknown option '%s'", name); return NGP_ERR_INVALID; }
     return NGP_OK;
 }
@@ -363,7 +335,7 @@ extern "C" int ngp_destroy(ngp_handle *h)
     cudaFree(h->d_envs); cudaFree(h->d_fb); cudaFree(h->d_rewards); cudaFree(h->d_frames); cudaFree(h->d_counters);
     cudaFree(h->d_genomes_stage); cudaFree(h->d_fitness_stage); cudaFree(h->d_hof_stage); cudaFree(h->d_hof_fit_stage);
     cudaFree(h->mlp_a); cudaFree(h->mlp_b); cudaFree(h->mlp_z); cudaFree(h->d_parent);
-    cudaFree(h->d_parked);
+    cudaFree(h->rank_keys); cudaFree(h->rank_idx);
     cudaFree(h->step_envs); cudaFree(h->step_x); cudaFree(h->step_act); cudaFree(h->step_opp);
     cudaFree(h->hof_hash_old); cudaFree(h->hof_hash_new); cudaFree(h->hof_order); cudaFree(h->hof_tmp_genomes); cudaFree(h->hof_tmp_fitness);
     cudaFreeHost(h->h_genomes); cudaFreeHost(h->h_fitness); cudaFreeHost(h->h_counters);
@@ -553,33 +525,9 @@ extern "C" int ngp_evaluate(ngp_handle *h, const float *genomes, int32_t n, cons
         h->prof_used++;
         NGP_CUDA(cudaEventRecord(ev0, st));
     }
-    // Tail compaction.  A generation lasts as long as its longest episode; once the queue is empty the resident warps thin out
-    // to a few live lanes each but keep sharing their schedulers.  When the launch holds more environments than one dense warp
-    // per scheduler can take (sm_count * 4 * 32), the first launch parks every unfinished environment as soon as fewer than
-    // that many are left, and a second launch of one-warp CTAs (full register budget) finishes them at single-warp latency.
-    const long long dense = (long long)h->sm_count * 4 * 32;
-    const bool compact = p.core && sync && total > 2 * dense && !h->opt_rollout_nocompact;
-    p.suspend_below = compact ? (int)dense : 0;
-    p.resume = 0;
-    p.parked = nullptr;
-    if (compact) {
-        const size_t need = (size_t)dense * sizeof(roll::Parked);
-        if (need > h->cap_parked) {
-            cudaFree(h->d_parked); h->d_parked = nullptr; h->cap_parked = 0;
-            NGP_CUDA(cudaMalloc(&h->d_parked, need));
-            h->cap_parked = need;
-        }
-        p.parked = (roll::Parked *)h->d_parked;
-    }
     kernel<<<(unsigned)blocks, block, smem, st>>>(p);
     h->launches++;
     NGP_CUDA(cudaGetLastError());
-    if (compact) {
-        p.suspend_below = 0; p.resume = 1;
-        rollout_kernel<1, false, 256><<<(unsigned)(dense / 32), 32, 32 * 32 * 4, st>>>(p);
-        h->launches++;
-        NGP_CUDA(cudaGetLastError());
-    }
     if (ev1) NGP_CUDA(cudaEventRecord(ev1, st));
     fitness_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(p.rewards, n, games, fitness);
     h->launches++;

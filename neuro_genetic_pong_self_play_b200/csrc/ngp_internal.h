@@ -33,7 +33,6 @@ struct ngp_handle {
     int32_t *d_frames;            // [cap_eval]
     unsigned long long *d_counters;   // [0] next env, [1] frames, [2] emulator errors
     int cap_eval;
-    void *d_parked; size_t cap_parked;    // environments parked between the two launches of a compacted evaluation (roll::Parked)
     // host staging (pinned) for the *_host entry points
     float *h_genomes; double *h_fitness; float *d_genomes_stage; double *d_fitness_stage;
     size_t stage_genomes, stage_fitness;
@@ -43,6 +42,7 @@ struct ngp_handle {
     // per-handle scratch of the operator entry points (nothing here is shared between handles)
     float *mlp_a, *mlp_b; double *mlp_z; size_t mlp_cap_ab, mlp_cap_z;      // ngp_mlp_forward activations
     int32_t *d_parent; size_t cap_parent;                                   // ngp_ga_step selection winners
+    void *rank_keys; int32_t *rank_idx; size_t cap_rank;                    // fitness ranking of the order-statistics tournament
     uint64_t *hof_hash_old, *hof_hash_new; int32_t *hof_order; float *hof_tmp_genomes; double *hof_tmp_fitness;   // ngp_hof_update
     size_t hof_cap_hash_old, hof_cap_hash_new, hof_cap_order, hof_cap_tmp_genomes, hof_cap_tmp_fitness;
     // ngp_evaluate for nets wider than the fused rollout (ngp_stepwise.cu): per-environment state, MLP input rows, actions,
@@ -52,7 +52,7 @@ struct ngp_handle {
     int fs_per_sm;                                                          // resident find_stuff CTAs per SM
     int tf32_attr_set;                                                      // dynamic shared memory opt-in done
     // ngp_set_option (tuning experiments; 0 = automatic)
-    int opt_rollout_block, opt_rollout_nosync, opt_rollout_lean, opt_rollout_blocks_per_sm, opt_mlp_no_tf32, opt_rollout_nocompact;
+    int opt_rollout_block, opt_rollout_nosync, opt_rollout_lean, opt_rollout_blocks_per_sm, opt_mlp_no_tf32, opt_select_os_min_t;
     // profiling of the rollout kernel
     int profile_on;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *prof_events;

@@ -617,6 +617,132 @@ __global__ void __launch_bounds__(256) select_tournament_kernel(const double *__
     if (lane == 0) parent_idx[slot] = best_idx;
 }
 
+// ---- selTournament for large populations: order statistics instead of N/4 draws per slot ----
+// The winner of a tournament of T independent uniform draws (with replacement) is the drawn individual of highest fitness.
+// With the population sorted by fitness (descending) the best rank R among T draws has P(R >= r) = ((N - r) / N)^T, so
+// R = floor(N * (1 - u^(1/T))) for one uniform u in (0, 1] has exactly the tournament's distribution; among individuals of
+// EQUAL fitness DEAP keeps the first drawn one, which is uniform over the tie group (draws are exchangeable): a second
+// uniform picks inside the group.  One Philox block per slot instead of T/4: O(N log^2 N) for the sort + O(N log N) for the
+// picks instead of O(N^2 / 4).  Same distribution as the draw-by-draw kernel, not the same draws, so it is only used on the
+// Philox path (never with injected draws) and only from `select_os_min_t` (default 8192) aspirants upwards.
+constexpr uint32_t STREAM_SELECT_OS = 0x53454C32u;
+
+__device__ __forceinline__ unsigned long long fitness_sort_key(double f)
+{
+    // monotone map of IEEE doubles to unsigned integers, then inverted: ascending key order = descending fitness
+    unsigned long long b = (unsigned long long)__double_as_longlong(f);
+    b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+    return ~b;
+}
+
+__global__ void rank_init_kernel(const double *__restrict__ fitness, int n, int n_pow2, unsigned long long *__restrict__ keys, int32_t *__restrict__ idx)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pow2) return;
+    keys[i] = i < n ? fitness_sort_key(fitness[i]) : ~0ull;          // padding sorts last
+    idx[i] = i < n ? i : 0x7FFFFFFF;
+}
+
+__device__ __forceinline__ bool rank_after(unsigned long long ka, int ia, unsigned long long kb, int ib)
+{
+    return ka > kb || (ka == kb && ia > ib);                         // ties: lower population index first
+}
+
+// bitonic sort, ascending in (key, index).  Steps with partner distance j < RANK_TILE run inside shared memory.
+constexpr int RANK_TILE = 2048;
+__global__ void __launch_bounds__(RANK_TILE / 2) rank_sort_tile_kernel(unsigned long long *__restrict__ keys, int32_t *__restrict__ idx, int k_first, int k_last)
+{
+    __shared__ unsigned long long sk[RANK_TILE];
+    __shared__ int32_t si[RANK_TILE];
+    const int base = blockIdx.x * RANK_TILE;
+    for (int t = threadIdx.x; t < RANK_TILE; t += blockDim.x) { sk[t] = keys[base + t]; si[t] = idx[base + t]; }
+    __syncthreads();
+    for (int k = k_first; k <= k_last; k <<= 1) {
+        for (int j = min(k >> 1, RANK_TILE >> 1); j > 0; j >>= 1) {
+            const int t = threadIdx.x;
+            const int a = 2 * t - (t & (j - 1)), b = a + j;          // the t-th pair with distance j
+            const bool up = (((base + a) & k) == 0);
+            const bool swap = rank_after(sk[a], si[a], sk[b], si[b]) == up;
+            if (swap) {
+                const unsigned long long tk = sk[a]; sk[a] = sk[b]; sk[b] = tk;
+                const int32_t ti = si[a]; si[a] = si[b]; si[b] = ti;
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < RANK_TILE; t += blockDim.x) { keys[base + t] = sk[t]; idx[base + t] = si[t]; }
+}
+
+__global__ void rank_sort_global_kernel(unsigned long long *__restrict__ keys, int32_t *__restrict__ idx, int n_pow2, int k, int j)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pow2 / 2) return;
+    const int a = 2 * t - (t & (j - 1)), b = a + j;
+    const bool up = ((a & k) == 0);
+    const unsigned long long ka = keys[a], kb = keys[b];
+    const int32_t ia = idx[a], ib = idx[b];
+    if (rank_after(ka, ia, kb, ib) == up) { keys[a] = kb; keys[b] = ka; idx[a] = ib; idx[b] = ia; }
+}
+
+__global__ void select_order_stat_kernel(const unsigned long long *__restrict__ keys, const int32_t *__restrict__ idx, int n, int k, int T, uint64_t seed,
+                                         uint64_t generation, int32_t *__restrict__ parent_idx)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= k) return;
+    uint32_t o[4];
+    pol::philox4x32((uint32_t)slot, 0u, (uint32_t)generation, STREAM_SELECT_OS, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    // u in (0, 1] with 53 bits; best rank among T uniform draws over n ranks
+    const double u = ((double)((((unsigned long long)o[0] << 32) | o[1]) >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+    long long r = (long long)floor((double)n * -expm1(log(u) / (double)T));
+    r = r < 0 ? 0 : (r > n - 1 ? n - 1 : r);
+    // tie group [lo, hi) of rank r in the sorted keys
+    const unsigned long long key = keys[r];
+    int lo = 0, hi = (int)r;                                         // first position with keys[pos] == key
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+    const int first = lo;
+    lo = (int)r; hi = n;                                             // first position with keys[pos] > key
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] <= key) lo = mid + 1; else hi = mid; }
+    const int count = lo - first;
+    const int pick = first + (int)(((unsigned long long)o[2] * (unsigned long long)count) >> 32);
+    parent_idx[slot] = idx[pick];
+}
+
+static int select_dispatch(ngp_handle *h, const double *fitness, int n, int k, int T, const int32_t *draws, uint64_t seed, uint64_t generation,
+                           int32_t *parent_idx, cudaStream_t st)
+{
+    const int min_t = h->opt_select_os_min_t > 0 ? h->opt_select_os_min_t : 8192;
+    if (draws || T < min_t) {
+        select_tournament_kernel<<<(unsigned)(((long long)k * 32 + 255) / 256), 256, 0, st>>>(fitness, n, k, T, draws, seed, generation, parent_idx);
+        h->launches++;
+        NGP_CUDA(cudaGetLastError());
+        return NGP_OK;
+    }
+    int n_pow2 = RANK_TILE;
+    while (n_pow2 < n) n_pow2 <<= 1;
+    if ((size_t)n_pow2 > h->cap_rank) {
+        cudaFree(h->rank_keys); cudaFree(h->rank_idx); h->rank_keys = nullptr; h->rank_idx = nullptr; h->cap_rank = 0;
+        NGP_CUDA(cudaMalloc(&h->rank_keys, (size_t)n_pow2 * sizeof(unsigned long long)));
+        NGP_CUDA(cudaMalloc(&h->rank_idx, (size_t)n_pow2 * sizeof(int32_t)));
+        h->cap_rank = n_pow2;
+    }
+    unsigned long long *keys = (unsigned long long *)h->rank_keys;
+    rank_init_kernel<<<(n_pow2 + 255) / 256, 256, 0, st>>>(fitness, n, n_pow2, keys, h->rank_idx);
+    rank_sort_tile_kernel<<<n_pow2 / RANK_TILE, RANK_TILE / 2, 0, st>>>(keys, h->rank_idx, 2, RANK_TILE);     // sorted tiles, alternating direction
+    h->launches += 2;
+    for (int kk = RANK_TILE * 2; kk <= n_pow2; kk <<= 1) {
+        for (int j = kk >> 1; j >= RANK_TILE; j >>= 1) {
+            rank_sort_global_kernel<<<(n_pow2 / 2 + 255) / 256, 256, 0, st>>>(keys, h->rank_idx, n_pow2, kk, j);
+            h->launches++;
+        }
+        rank_sort_tile_kernel<<<n_pow2 / RANK_TILE, RANK_TILE / 2, 0, st>>>(keys, h->rank_idx, kk, kk);        // distances below the tile size
+        h->launches++;
+    }
+    select_order_stat_kernel<<<(k + 255) / 256, 256, 0, st>>>(keys, h->rank_idx, n, k, T, seed, generation, parent_idx);
+    h->launches++;
+    NGP_CUDA(cudaGetLastError());
+    return NGP_OK;
+}
+
 // varAnd: clone selected parents, blend-crossover pairs (0,1),(2,3).., then Gaussian mutation.
 // One thread per (pair, gene).  Every FP32 operation is individually rounded (no FMA contraction) so
 // that, given injected noise, the children match the numpy restatement bit-for-bit.
@@ -698,9 +824,10 @@ extern "C" int ngp_ga_step(ngp_handle *h, const float *genomes, const double *fi
         h->launches++;
         NGP_CUDA(cudaGetLastError());
     }
-    select_tournament_kernel<<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(fitness, n, n, T, nz.sel_draws, seed, generation, parent_idx);
-    h->launches++;
-    NGP_CUDA(cudaGetLastError());
+    {
+        const int rc = select_dispatch(h, fitness, n, n, T, nz.sel_draws, seed, generation, parent_idx, st);
+        if (rc != NGP_OK) return rc;
+    }
     const long long work = (long long)((n + 1) / 2) * h->gene_size;
     vary_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(genomes, parent_idx, n, h->gene_size, nz, seed, generation, h->cfg.cxpb,
                                                                h->cfg.cx_alpha, h->cfg.mutpb, h->cfg.mut_mu, h->cfg.mut_sigma,
@@ -717,11 +844,7 @@ extern "C" int ngp_select(ngp_handle *h, const double *fitness, int32_t n, int32
     NGP_CUDA(cudaSetDevice(h->device));
     int T = h->cfg.tournament_size;
     if (T < 1) T = 1;
-    select_tournament_kernel<<<(unsigned)(((long long)k * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fitness, n, k, T, draws, seed, generation,
-                                                                                                     parent_idx);
-    h->launches++;
-    NGP_CUDA(cudaGetLastError());
-    return NGP_OK;
+    return select_dispatch(h, fitness, n, k, T, draws, seed, generation, parent_idx, (cudaStream_t)stream);
 }
 
 extern "C" int ngp_init_population(ngp_handle *h, float *genomes, int32_t n, uint64_t seed, void *stream)

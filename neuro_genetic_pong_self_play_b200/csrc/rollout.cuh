@@ -85,12 +85,7 @@ struct RolloutParams {
     pol::Shape shape;
     double *rewards;                // [n*games]
     int32_t *frames;                // [n*games]
-    unsigned long long *counters;   // [0] next env, [1] frames, [2] errors, [3] finished episodes, [4] suspended environments
-    // tail compaction (ngp_core.cu: ngp_evaluate): a launch with suspend_below > 0 parks every unfinished environment in
-    // `parked` and exits once fewer than that many episodes are unfinished; the follow-up launch (resume = 1) picks them up
-    // with one dense warp per scheduler.
-    int suspend_below, resume;
-    struct Parked *parked;
+    unsigned long long *counters;   // [0] next env, [1] frames, [2] errors
 };
 
 struct EnvPlan {
@@ -151,12 +146,6 @@ struct Episode {
     double last_ball[2];
     int left_act, right_act;
     EnvPlan plan;
-};
-
-// an environment taken out of one launch and continued by the next (state between two frames)
-struct Parked {
-    Snapshot snap;
-    Episode ep;
 };
 
 __device__ __forceinline__ void episode_begin(Episode &ep, const RolloutParams &p, int e, Chip &s, CpuRegs &r, Ram ram)

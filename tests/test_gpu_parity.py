@@ -394,32 +394,6 @@ def test_find_stuff_kernel_dense_random_frames(engine):
         assert np.array_equal(loc[i][rv == 1], rl[rv == 1].astype(np.float32)), i
 
 
-def test_tail_compaction_gives_the_same_bits(ngp):
-    """Launches with more environments than one dense warp per scheduler park the unfinished episodes once few are left and
-    finish them in a second launch (csrc/ngp_core.cu 'tail compaction'): rewards, frame counts and fitness must not change."""
-    n = 8192                                           # 49 152 environments > 2 x 148 x 4 x 32
-    cfg = ngp.Config(SCHEDULE=ngp.SCHEDULE_ROUND_ROBIN, POPULATION_SIZE=n)
-    eng = ngp.Engine(cfg, device=0)
-    genomes = eng.init_population(n, seed=3)
-    genomes[: n // 2] = (genomes[: n // 2] - 0.5) * 6.0          # half the population with signed weights: varied episode lengths
-    a = eng.evaluate(genomes, seed=2, generation=1, want_detail=True)
-    before = eng.launches
-    b = eng.evaluate(genomes, seed=2, generation=1, want_detail=True)
-    assert eng.launches - before == 3                  # rollout, resumed rollout, fitness reduction
-    eng.set_option("rollout_nocompact", 1)
-    try:
-        before = eng.launches
-        c = eng.evaluate(genomes, seed=2, generation=1, want_detail=True)
-        assert eng.launches - before == 2
-    finally:
-        eng.set_option("rollout_nocompact", 0)
-    for key in ("fitness", "rewards", "frames"):
-        assert torch.equal(a[key], b[key]) and torch.equal(a[key], c[key]), key
-    assert a["frames_total"] == c["frames_total"] == int(a["frames"].sum().item())
-    assert a["frames"].max().item() > 2 * a["frames"].float().mean().item()      # there is a tail to compact
-    eng.close()
-
-
 @pytest.mark.parametrize("core", [0, 1])
 def test_cuda_core_reproduces_obs_npy_pixel_for_pixel(engine, obs_npy, core):
     """The committed button trace (tests/golden/obs_trace.npz) through ngp_env_step: the frame equals the reference's real

@@ -139,6 +139,69 @@ def test_philox_ga_path_matches_restated_counter_layout(ngp, n):
     eng.close()
 
 
+def test_order_statistics_tournament(ngp):
+    """selTournament for large populations (csrc/ngp_ops.cu select_order_stat_kernel): winners drawn from the order statistics
+    of the tournament on the fitness-sorted population.  Checked: (1) the counter layout and arithmetic restated with numpy
+    reproduce the device picks; (2) the winners' rank distribution is the tournament's P(R >= r) = ((N - r) / N)^T, and equals
+    the draw-by-draw kernel's statistically; (3) equal fitness: uniform inside the tie group; (4) config 5 scale runs."""
+    import oracle
+    n, T = 4096, 1024
+    cfg = ngp.Config(POPULATION_SIZE=n)                      # TOURNAMENT_SIZE = n // 4
+    eng = ngp.Engine(cfg, device=0)
+    rng = np.random.RandomState(12)
+    fitness = np.round(rng.standard_normal(n), 2)            # many ties
+    seed, gen, k = 0xABCDEF0123, 5, 200_000
+    eng.set_option("select_os_min_t", 1)
+    got = eng.select(_cuda(fitness), k, seed=seed, generation=gen).cpu().numpy()
+    # (1) restatement: stable sort by (-fitness, index); one Philox block per slot
+    order = np.lexsort((np.arange(n), -fitness))
+    fs = fitness[order]
+    w0, w1, w2, _ = oracle.philox4x32_np(np.arange(k, dtype=np.uint64), 0, gen, 0x53454C32, seed)
+    u = ((((w0.astype(np.uint64) << np.uint64(32)) | w1.astype(np.uint64)) >> np.uint64(11)).astype(np.float64) + 1.0) / 9007199254740992.0
+    r = np.clip(np.floor(n * -np.expm1(np.log(u) / T)).astype(np.int64), 0, n - 1)
+    first = np.searchsorted(-fs, -fs[r], side="left"); last = np.searchsorted(-fs, -fs[r], side="right")
+    pick = first + ((w2.astype(np.uint64) * (last - first).astype(np.uint64)) >> np.uint64(32)).astype(np.int64)
+    want = order[pick]
+    assert (got == want).mean() > 0.9999                     # log/expm1 may round differently at a rank boundary once in a while
+    assert np.array_equal(fitness[got], fitness[want]) or (fitness[got] != fitness[want]).mean() < 1e-4
+    # (2) rank distribution against the closed form and against the draw-by-draw kernel
+    rank_of = np.empty(n, np.int64); rank_of[order] = np.arange(n)
+    group_first = np.searchsorted(-fs, -fs, side="left")      # first rank of each individual's tie group
+    g_got = group_first[rank_of[got]]
+    eng.set_option("select_os_min_t", 0)
+    ref = eng.select(_cuda(fitness), 50_000, seed=seed, generation=gen).cpu().numpy()        # T < 8192: N/4 Philox draws per slot
+    g_ref = group_first[rank_of[ref]]
+    edges = np.unique(group_first)
+    cdf = 1.0 - ((n - edges) / n) ** T                       # P(best group starts before edge)
+    cdf = np.append(cdf, 1.0)
+    for sample in (g_got, g_ref):
+        emp = np.searchsorted(np.sort(sample), edges, side="left") / len(sample)
+        assert np.abs(np.append(emp, 1.0) - cdf).max() < 4.0 / np.sqrt(len(sample))          # Kolmogorov-Smirnov style bound
+    # (3) uniform inside the best tie group
+    top = np.nonzero(fitness == fitness.max())[0]
+    if len(top) == 1:
+        fitness[rng.choice(n, 7, replace=False)] = fitness.max(); top = np.nonzero(fitness == fitness.max())[0]
+        eng.set_option("select_os_min_t", 1)
+        got = eng.select(_cuda(fitness), k, seed=seed, generation=gen + 1).cpu().numpy()
+    winners = got[np.isin(got, top)]
+    counts = np.array([(winners == t).sum() for t in top])
+    assert len(winners) > 1000 and np.abs(counts / len(winners) - 1.0 / len(top)).max() < 5.0 / np.sqrt(len(winners))
+    eng.close()
+    # (4) BASELINE config 5's largest population: one GA step on 2^20 genomes uses the order statistics by default
+    n = 1 << 20
+    eng = ngp.Engine(ngp.Config(POPULATION_SIZE=n), device=0)
+    pop = eng.init_population(n, seed=1)
+    fit = _cuda(np.random.RandomState(1).standard_normal(n))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.ga_step(pop, fit, seed=3, generation=0)
+    ev0.record(); out = eng.ga_step(pop, fit, seed=3, generation=1); ev1.record(); torch.cuda.synchronize()
+    parents = out["parent_idx"].cpu().numpy()
+    assert parents.min() >= 0 and parents.max() < n
+    best_ranks = np.argsort(np.argsort(-fit.cpu().numpy()))[parents]
+    assert np.median(best_ranks) < 8 and ev0.elapsed_time(ev1) < 50.0        # T = 262144: winners are the top few; was 945 ms draw by draw
+    eng.close()
+
+
 def test_philox_hof_pick_matches_restated_counter_layout(ngp):
     """Games 3..5 with the hall-of-fame opponent drawn by Philox equal the same evaluation with the restated picks injected."""
     import oracle
