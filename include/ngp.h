@@ -124,6 +124,15 @@ int ngp_find_stuff(ngp_handle *h, const uint8_t *frames, int32_t n, float *loc, 
 int ngp_mlp_forward(ngp_handle *h, const float *genomes, const float *x, int32_t n_genomes, int32_t envs,
                     uint8_t *act, float *out, void *stream);
 
+/* Two-call form for a genome set that is used for many forward passes (the reference builds a NeuralNetwork once per
+ * individual -- __init__/populate_weights, numpy_nn.py:35-69, main.py:29 -- and calls run() every frame):
+ * ngp_mlp_prepare re-lays the wide hidden layers of `genomes` out once (handle-owned copy; a snapshot, like the reference's
+ * populate_weights: later changes to `genomes` are not seen), ngp_mlp_forward_prepared then streams those weights from HBM
+ * straight into tensor memory.  Same arguments and results as ngp_mlp_forward; genomes / n_genomes must be the prepared ones. */
+int ngp_mlp_prepare(ngp_handle *h, const float *genomes, int32_t n_genomes, void *stream);
+int ngp_mlp_forward_prepared(ngp_handle *h, const float *genomes, const float *x, int32_t n_genomes, int32_t envs,
+                             uint8_t *act, float *out, void *stream);
+
 /* ---- fused hot path: population genomes in -> fitness out.  Replaces
  * toolbox.map(toolbox.evaluate, population) (ga.py:83, main.py:28-66, main.py:69-154).
  * genomes: device f32[n][G].  hof_genomes f32[n_hof][G], hof_fitness f64[n_hof] (device; may be

@@ -20,7 +20,7 @@ EXPORTS = [
     "ngp_env_reset", "ngp_env_step", "ngp_env_step_core", "ngp_env_digest", "ngp_find_stuff", "ngp_mlp_forward", "ngp_evaluate",
     "ngp_evaluate_host", "ngp_ga_step", "ngp_init_population", "ngp_launch_count", "ngp_profile_enable", "ngp_profile_read",
     "ngp_config_size", "ngp_set_option", "ngp_select", "ngp_mate", "ngp_mutate", "ngp_hof_update", "ngp_exchange_bytes",
-    "ngp_pack_elites", "ngp_unpack_elites",
+    "ngp_pack_elites", "ngp_unpack_elites", "ngp_mlp_prepare", "ngp_mlp_forward_prepared",
 ]
 
 
@@ -79,6 +79,8 @@ def load(build_if_missing: bool = True):
     L.ngp_env_digest.argtypes = [vp, vp, vp]
     L.ngp_find_stuff.argtypes = [vp, vp, i32, vp, vp, vp]
     L.ngp_mlp_forward.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+    L.ngp_mlp_prepare.argtypes = [vp, vp, i32, vp]
+    L.ngp_mlp_forward_prepared.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
     L.ngp_evaluate.argtypes = [vp, vp, i32, vp, vp, i32, vp, u64, u64, vp, vp, vp, ctypes.POINTER(u64), vp]
     L.ngp_evaluate_host.argtypes = [vp, vp, i32, vp, vp, i32, u64, u64, vp, ctypes.POINTER(u64)]
     L.ngp_ga_step.argtypes = [vp, vp, vp, i32, u64, u64, ctypes.POINTER(NgpNoise), vp, vp, vp, vp, vp]

@@ -335,7 +335,7 @@ extern "C" int ngp_destroy(ngp_handle *h)
     cudaFree(h->d_envs); cudaFree(h->d_fb); cudaFree(h->d_rewards); cudaFree(h->d_frames); cudaFree(h->d_counters);
     cudaFree(h->d_genomes_stage); cudaFree(h->d_fitness_stage); cudaFree(h->d_hof_stage); cudaFree(h->d_hof_fit_stage);
     cudaFree(h->mlp_a); cudaFree(h->mlp_b); cudaFree(h->mlp_z); cudaFree(h->d_parent);
-    cudaFree(h->rank_keys); cudaFree(h->rank_idx);
+    cudaFree(h->rank_keys); cudaFree(h->rank_idx); cudaFree(h->prep_packed);
     cudaFree(h->step_envs); cudaFree(h->step_x); cudaFree(h->step_act); cudaFree(h->step_opp);
     cudaFree(h->hof_hash_old); cudaFree(h->hof_hash_new); cudaFree(h->hof_order); cudaFree(h->hof_tmp_genomes); cudaFree(h->hof_tmp_fitness);
     cudaFreeHost(h->h_genomes); cudaFreeHost(h->h_fitness); cudaFreeHost(h->h_counters);

@@ -49,6 +49,8 @@ struct ngp_handle {
     // gathered hall-of-fame opponents
     void *step_envs; float *step_x; uint8_t *step_act; float *step_opp;
     size_t step_cap_envs, step_cap_x, step_cap_act, step_cap_opp;
+    // ngp_mlp_prepare: packed wide layers of the prepared genome set (ngp_mlp_tmem.cu)
+    float *prep_packed; size_t prep_cap, prep_per_genome; const float *prep_src; int prep_n; int tmem_attr_set;
     int fs_per_sm;                                                          // resident find_stuff CTAs per SM
     int tf32_attr_set;                                                      // dynamic shared memory opt-in done
     // ngp_set_option (tuning experiments; 0 = automatic)

@@ -1,0 +1,364 @@
+// ngp_mlp_tmem.cu -- K3 wide hidden layers, second generation: weights prepared once per genome set (the reference's
+// NeuralNetwork.__init__/populate_weights, /root/reference/numpy_nn.py:35-69, runs once per individual and `run` many times
+// per episode, main.py:29,84-90), then streamed straight from HBM into TENSOR MEMORY as the A operand of tcgen05.mma.
+//
+// Why: the first-generation layer (ngp_mlp_tf32.cu) stages raw FP32 weight tiles in shared memory, reads them back, writes
+// hi/lo tiles and lets the tensor core read those three times: ~10 bytes of shared-memory traffic per weight byte, which is
+// the SM's shared-memory bandwidth at 2.3 TB/s of weights (profiles/README.md).  Here a weight never touches shared memory:
+//
+//   ngp_mlp_prepare   packs every wide layer of every genome into 128-output x 16-k tiles  [tile][q][row][4 floats]  (one
+//                     coalesced 16-byte load per thread and quarter-chunk) and the bias weights into their own vector
+//   A producers       4 warps, thread = output row (= TMEM lane): LDG.128 x 4 per chunk, PF chunks ahead in registers,
+//                     split  w = hi + lo  (hi = tf32-truncated), tcgen05.st hi and lo into a 4-stage ring of TMEM columns
+//   B producers       4 warps: activations [env][k] (L2-resident, 16-byte aligned rows) -> registers -> hi/lo tiles in shared
+//                     memory in the canonical no-swizzle K-major core-matrix layout (the only shared-memory traffic left)
+//   MMA warp          per chunk and k-step of 8:  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  ("3xTF32", error ~2^-21) with A from
+//                     TMEM and B from shared memory; tcgen05.commit hands the stage back to both producer groups
+//   epilogue          the A producers (their warp owns the TMEM lanes of its rows): tcgen05.ld, + bias, sigmoid, coalesced stores
+//
+// D^T form as before: M = 128 outputs, N = TN environments (64 or 128: with 128 a genome's weights are streamed once for the
+// 2 x 64 rows of the round-robin stepwise evaluation), K = fan-in (bias handled in the epilogue, so K = 512 exactly for the
+// flagship net).  TMEM: TN accumulator columns + 4 stages x (16 hi + 16 lo) columns = 256 -> two CTAs per SM.
+#include "ngp_internal.h"
+
+namespace tmm {
+
+constexpr int TM = 128, KC = 16, STAGES = 4, PF = 3;
+constexpr uint32_t SBO = 128;
+constexpr uint32_t TMEM_COLS = 256;
+constexpr int A_THREADS = 128, B_THREADS = 128, THREADS = A_THREADS + B_THREADS + 32;
+
+__host__ __device__ constexpr uint32_t lbo(int TN) { return (uint32_t)TN * 16u + 16u; }            // +16 B: conflict-free stores
+__host__ __device__ constexpr uint32_t tile_b(int TN) { return (KC / 4) * lbo(TN); }               // one of B_hi / B_lo
+__host__ __device__ constexpr uint32_t stage_b(int TN) { return 2 * tile_b(TN); }
+__host__ __device__ constexpr uint32_t smem_bytes(int TN) { return STAGES * stage_b(TN) + 128; }
+__host__ __device__ constexpr uint32_t idesc(int TN)
+{
+    // cute::UMMA::InstrDescriptor: D=F32 (bit 4), A=B=TF32 (2 at bits 7, 10), both K-major, N>>3 at 17, M>>4 at 24
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes)
+{
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t id, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(id), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+                   "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ float4 ldg_stream(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t tf32_hi(float v) { return __float_as_uint(v) & 0xFFFFE000u; }
+
+// packed layout of one genome's layer: tiles[ob][c][q][row][4]  (ob = 128-output block, c = 16-k chunk, q = quarter of the chunk)
+// followed by bias[ob * 128 + row]; rows / k beyond the layer are zero
+__host__ __device__ inline size_t packed_floats(int ni, int no)
+{
+    const size_t OB = (no + TM - 1) / TM, NC = (ni + KC - 1) / KC;
+    return OB * NC * (size_t)(KC * TM) + OB * TM;
+}
+
+__global__ void __launch_bounds__(256) mlp_pack_layer_kernel(const float *__restrict__ genomes, size_t w_off, int G, int ni, int no, int bias,
+                                                             float *__restrict__ packed, size_t per_genome, size_t layer_off)
+{
+    const int OB = (no + TM - 1) / TM, NC = (ni + KC - 1) / KC, K = ni + bias;
+    const int g = blockIdx.y;
+    const float *W = genomes + (size_t)g * G + w_off;
+    float *dst = packed + (size_t)g * per_genome + layer_off;
+    const long long units = (long long)OB * NC * 4 * TM;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < units + (long long)OB * TM; u += (long long)gridDim.x * blockDim.x) {
+        if (u < units) {
+            const int row = (int)(u % TM), q = (int)((u / TM) % 4), c = (int)((u / (TM * 4)) % NC), ob = (int)(u / ((long long)TM * 4 * NC));
+            const int o = ob * TM + row, k0 = c * KC + q * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (o < no) {
+                const float *src = W + (size_t)o * K + k0;
+                if (k0 + 0 < ni) v.x = __ldg(src + 0);
+                if (k0 + 1 < ni) v.y = __ldg(src + 1);
+                if (k0 + 2 < ni) v.z = __ldg(src + 2);
+                if (k0 + 3 < ni) v.w = __ldg(src + 3);
+            }
+            reinterpret_cast<float4 *>(dst)[u] = v;
+        } else {
+            const int o = (int)(u - units);
+            dst[units * 4 + o] = (bias && o < no) ? __ldg(W + (size_t)o * K + ni) : 0.f;
+        }
+    }
+}
+
+template <int TN>
+__global__ void __launch_bounds__(THREADS, 2)
+mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_t layer_off, const float *__restrict__ in, int envs, int ni, int no,
+                      float *__restrict__ out)
+{
+    constexpr uint32_t LBO = lbo(TN), TILE_B = tile_b(TN), STAGE_B = stage_b(TN), IDESC = idesc(TN);
+    constexpr int B_UNITS = TN * (KC / 4) / B_THREADS;                   // 16-byte units of a B chunk per producer thread (4 or 2)
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.z, e0 = blockIdx.y * TN, ob = blockIdx.x;
+    const int NC = (ni + KC - 1) / KC;
+    const uint32_t smem_base = smem_u32(smem);
+    // barriers: a_full[s] (4 warps), b_full[s] (4 warps), free[s] (one commit), done
+    const uint32_t bar_a = smem_base + STAGES * STAGE_B, bar_b = bar_a + 8 * STAGES, bar_free = bar_b + 8 * STAGES, bar_done = bar_free + 8 * STAGES;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_a + 8 * s, A_THREADS / 32); mbar_init(bar_b + 8 * s, B_THREADS / 32); mbar_init(bar_free + 8 * s, 1); }
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_slot;                              // columns [0, TN): accumulator
+    const uint32_t tmem_a = tmem_d + 128;                                // columns [128, 256): 4 stages x (16 hi + 16 lo)
+
+    if (warp < A_THREADS / 32) {
+        // ------------------------------- A producers: thread = output row = TMEM lane -------------------------------
+        const float4 *src = reinterpret_cast<const float4 *>(packed + (size_t)g * per_genome + layer_off) + (size_t)ob * NC * (4 * TM) + tid;
+        float4 pre[PF][4];
+#pragma unroll
+        for (int p = 0; p < PF; ++p)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pre[p][q] = p < NC ? ldg_stream(src + ((size_t)p * 4 + q) * TM) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t lane_addr = tmem_a + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < NC; c0 += PF) {
+#pragma unroll
+            for (int p = 0; p < PF; ++p) {
+                const int c = c0 + p;
+                if (c < NC) {
+                    const int s = c % STAGES;
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 v = pre[p][q];
+                        hi[4 * q + 0] = tf32_hi(v.x); lo[4 * q + 0] = __float_as_uint(v.x - __uint_as_float(hi[4 * q + 0]));
+                        hi[4 * q + 1] = tf32_hi(v.y); lo[4 * q + 1] = __float_as_uint(v.y - __uint_as_float(hi[4 * q + 1]));
+                        hi[4 * q + 2] = tf32_hi(v.z); lo[4 * q + 2] = __float_as_uint(v.z - __uint_as_float(hi[4 * q + 2]));
+                        hi[4 * q + 3] = tf32_hi(v.w); lo[4 * q + 3] = __float_as_uint(v.w - __uint_as_float(hi[4 * q + 3]));
+                    }
+                    const int cn = c + PF;                               // refill the register slot
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (cn < NC) pre[p][q] = ldg_stream(src + ((size_t)cn * 4 + q) * TM);
+                    if (c >= STAGES) {                                   // the MMAs that read this stage STAGES chunks ago are done
+                        mbar_wait(bar_free + 8 * s, ((c / STAGES) - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    tmem_st16(lane_addr + (uint32_t)(s * 32), hi);
+                    tmem_st16(lane_addr + (uint32_t)(s * 32 + 16), lo);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_a + 8 * s);
+                }
+            }
+        }
+    } else if (warp < (A_THREADS + B_THREADS) / 32) {
+        // ------------------------------- B producers: activations -> hi/lo tiles in shared memory -------------------------------
+        const int t = tid - A_THREADS;
+        const int cu = t & 3, r0 = t >> 2;                               // k-unit of the chunk, first row; rows r0 + 32 j
+        const float *A = in + (size_t)g * envs * ni;
+        float4 pre[PF][B_UNITS];
+        auto fetch = [&](int c, float4 (&dst)[B_UNITS]) {
+#pragma unroll
+            for (int j = 0; j < B_UNITS; ++j) {
+                const int row = e0 + r0 + 32 * j, k = c * KC + cu * 4;
+                dst[j] = (c < NC && row < envs && k < ni) ? __ldg(reinterpret_cast<const float4 *>(A + (size_t)row * ni + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+#pragma unroll
+        for (int p = 0; p < PF; ++p) fetch(p, pre[p]);
+#pragma unroll 1
+        for (int c0 = 0; c0 < NC; c0 += PF) {
+#pragma unroll
+            for (int p = 0; p < PF; ++p) {
+                const int c = c0 + p;
+                if (c < NC) {
+                    const int s = c % STAGES;
+                    if (c >= STAGES) mbar_wait(bar_free + 8 * s, ((c / STAGES) - 1) & 1);
+                    uint8_t *stage = smem + s * STAGE_B;
+#pragma unroll
+                    for (int j = 0; j < B_UNITS; ++j) {
+                        const int r = r0 + 32 * j;
+                        const float4 v = pre[p][j];
+                        float4 h, l;
+                        h.x = __uint_as_float(tf32_hi(v.x)); l.x = v.x - h.x;
+                        h.y = __uint_as_float(tf32_hi(v.y)); l.y = v.y - h.y;
+                        h.z = __uint_as_float(tf32_hi(v.z)); l.z = v.z - h.z;
+                        h.w = __uint_as_float(tf32_hi(v.w)); l.w = v.w - h.w;
+                        uint8_t *dst = stage + cu * LBO + (r >> 3) * SBO + (r & 7) * 16;
+                        *reinterpret_cast<float4 *>(dst) = h;
+                        *reinterpret_cast<float4 *>(dst + TILE_B) = l;
+                    }
+                    fetch(c + PF, pre[p]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_b + 8 * s);
+                }
+            }
+        }
+    } else {
+        // ------------------------------- MMA warp -------------------------------
+        if (lane == 0) {
+            for (int c = 0; c < NC; ++c) {
+                const int s = c % STAGES;
+                const uint32_t ph = (c / STAGES) & 1;
+                mbar_wait(bar_a + 8 * s, ph);
+                mbar_wait(bar_b + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = tmem_a + (uint32_t)(s * 32), a_lo = a_hi + 16;
+                const uint32_t b_hi = smem_base + s * STAGE_B, b_lo = b_hi + TILE_B;
+#pragma unroll
+                for (int j = 0; j < KC / 8; ++j) {
+                    const uint32_t kb = 2 * j * LBO;
+                    umma_ts(tmem_d, a_lo + 8 * j, make_desc(b_hi + kb, LBO), IDESC, (c | j) ? 1u : 0u);       // small terms first
+                    umma_ts(tmem_d, a_hi + 8 * j, make_desc(b_lo + kb, LBO), IDESC, 1u);
+                    umma_ts(tmem_d, a_hi + 8 * j, make_desc(b_hi + kb, LBO), IDESC, 1u);
+                }
+                umma_commit(bar_free + 8 * s);
+                if (c == NC - 1) umma_commit(bar_done);
+            }
+        }
+        __syncwarp();
+    }
+    // ------------------------------- epilogue: the A producers own the TMEM lanes of their rows -------------------------------
+    if (warp < A_THREADS / 32) {
+        mbar_wait(bar_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int o = ob * TM + tid;
+        const float b = packed[(size_t)g * per_genome + layer_off + (size_t)((no + TM - 1) / TM) * NC * (KC * TM) + o];
+#pragma unroll 1
+        for (int half = 0; half < TN / 32; ++half) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(half * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                  "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                  "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (o < no) {
+                float *dst = out + ((size_t)g * envs + e0 + half * 32) * no + o;
+                const int e_left = envs - (e0 + half * 32);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (j < e_left) *dst = __frcp_rn(1.0f + __expf(-(__uint_as_float(v[j]) + b)));
+                    dst += no;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+}
+
+}  // namespace tmm
+
+// which layers of the handle's network run on the prepared (packed) path
+static bool layer_is_packed(const pol::Shape &sh, int l)
+{
+    const int L = sh.n_layers - 1;              // hidden layers with a real contraction and 16-byte aligned activation rows
+    return l != L - 1 && sh.nodes[l] >= 64 && sh.nodes[l + 1] >= 64 && sh.nodes[l] % 4 == 0;
+}
+
+// ngp_mlp_prepare: see include/ngp.h
+extern "C" int ngp_mlp_prepare(ngp_handle *h, const float *genomes, int32_t n_genomes, void *stream)
+{
+    NGP_REQUIRE(h && genomes && n_genomes > 0, "ngp_mlp_prepare: bad arguments");
+    NGP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const pol::Shape &sh = h->shape;
+    const int bias = sh.bias ? 1 : 0, L = sh.n_layers - 1;
+    size_t per_genome = 0;
+    for (int l = 0; l < L; ++l)
+        if (layer_is_packed(sh, l)) per_genome += tmm::packed_floats(sh.nodes[l], sh.nodes[l + 1]);
+    h->prep_n = 0; h->prep_src = nullptr; h->prep_per_genome = per_genome;
+    if (per_genome == 0) { h->prep_n = n_genomes; h->prep_src = genomes; return NGP_OK; }      // nothing to pack for this network
+    const size_t need = per_genome * (size_t)n_genomes * sizeof(float);
+    if (need > h->prep_cap) {
+        cudaFree(h->prep_packed); h->prep_packed = nullptr; h->prep_cap = 0;
+        NGP_CUDA(cudaMalloc(&h->prep_packed, need));
+        h->prep_cap = need;
+    }
+    size_t w_off = 0, layer_off = 0;
+    for (int l = 0; l < L; ++l) {
+        const int ni = sh.nodes[l], no = sh.nodes[l + 1];
+        if (layer_is_packed(sh, l)) {
+            dim3 grid(128, n_genomes);
+            tmm::mlp_pack_layer_kernel<<<grid, 256, 0, st>>>(genomes, w_off, h->gene_size, ni, no, bias, h->prep_packed, per_genome, layer_off);
+            h->launches++;
+            NGP_CUDA(cudaGetLastError());
+            layer_off += tmm::packed_floats(ni, no);
+        }
+        w_off += (size_t)(ni + bias) * no;
+    }
+    h->prep_n = n_genomes; h->prep_src = genomes;
+    return NGP_OK;
+}
+
+// one prepared wide hidden layer (called by ngp_mlp_forward_prepared); NGP_ERR_UNSUPPORTED -> the caller uses the unprepared path
+int ngp_mlp_layer_tmem(ngp_handle *h, int l, const float *in, int n_genomes, int envs, float *out, cudaStream_t st)
+{
+    const pol::Shape &sh = h->shape;
+    if (!layer_is_packed(sh, l) || envs < 16 || !h->prep_packed) return NGP_ERR_UNSUPPORTED;
+    size_t layer_off = 0;
+    for (int i = 0; i < l; ++i)
+        if (layer_is_packed(sh, i)) layer_off += tmm::packed_floats(sh.nodes[i], sh.nodes[i + 1]);
+    const int ni = sh.nodes[l], no = sh.nodes[l + 1];
+    if (!h->tmem_attr_set) {
+        NGP_CUDA(cudaFuncSetAttribute(tmm::mlp_layer_tmem_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmm::smem_bytes(64)));
+        NGP_CUDA(cudaFuncSetAttribute(tmm::mlp_layer_tmem_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tmm::smem_bytes(128)));
+        h->tmem_attr_set = 1;
+    }
+    if (envs > 64) {
+        dim3 grid((no + tmm::TM - 1) / tmm::TM, (envs + 127) / 128, n_genomes);
+        tmm::mlp_layer_tmem_kernel<128><<<grid, tmm::THREADS, tmm::smem_bytes(128), st>>>(h->prep_packed, h->prep_per_genome, layer_off, in, envs, ni, no, out);
+    } else {
+        dim3 grid((no + tmm::TM - 1) / tmm::TM, 1, n_genomes);
+        tmm::mlp_layer_tmem_kernel<64><<<grid, tmm::THREADS, tmm::smem_bytes(64), st>>>(h->prep_packed, h->prep_per_genome, layer_off, in, envs, ni, no, out);
+    }
+    h->launches++;
+    NGP_CUDA(cudaGetLastError());
+    return NGP_OK;
+}

@@ -448,8 +448,27 @@ int ngp_mlp_layer_tf32(ngp_handle *h, const float *genomes, size_t w_off, const 
 
 struct MlpScratch { float *&a, *&b; double *&z; size_t &cap_ab, &cap_z; };     // view of the handle's scratch
 
+int ngp_mlp_layer_tmem(ngp_handle *h, int l, const float *in, int n_genomes, int envs, float *out, cudaStream_t st);    // ngp_mlp_tmem.cu
+
+static int mlp_forward_impl(ngp_handle *h, const float *genomes, const float *x, int32_t n_genomes, int32_t envs, uint8_t *act, float *out,
+                            void *stream, bool prepared);
+
 extern "C" int ngp_mlp_forward(ngp_handle *h, const float *genomes, const float *x, int32_t n_genomes, int32_t envs, uint8_t *act,
                                float *out, void *stream)
+{
+    return mlp_forward_impl(h, genomes, x, n_genomes, envs, act, out, stream, false);
+}
+
+extern "C" int ngp_mlp_forward_prepared(ngp_handle *h, const float *genomes, const float *x, int32_t n_genomes, int32_t envs, uint8_t *act,
+                                        float *out, void *stream)
+{
+    NGP_REQUIRE(h && h->prep_src == genomes && h->prep_n == n_genomes && n_genomes > 0,
+                "ngp_mlp_forward_prepared: call ngp_mlp_prepare on these genomes first");
+    return mlp_forward_impl(h, genomes, x, n_genomes, envs, act, out, stream, true);
+}
+
+static int mlp_forward_impl(ngp_handle *h, const float *genomes, const float *x, int32_t n_genomes, int32_t envs, uint8_t *act, float *out,
+                            void *stream, bool prepared)
 {
     NGP_REQUIRE(h && genomes && x && act && n_genomes > 0 && envs > 0, "ngp_mlp_forward: bad arguments");
     NGP_CUDA(cudaSetDevice(h->device));
@@ -507,6 +526,12 @@ extern "C" int ngp_mlp_forward(ngp_handle *h, const float *genomes, const float 
             h->launches++;
             NGP_CUDA(cudaGetLastError());
             launched = true;
+        }
+        if (!launched && prepared && l != L - 1 && !h->opt_mlp_no_tf32) {
+            // prepared genome set: weights stream from HBM straight into tensor memory (ngp_mlp_tmem.cu)
+            const int rc = ngp_mlp_layer_tmem(h, l, in, n_genomes, envs, bufs[l & 1], st);
+            if (rc == NGP_OK) launched = true;
+            else if (rc != NGP_ERR_UNSUPPORTED) return rc;
         }
         if (!launched && l != L - 1 && !h->opt_mlp_no_tf32) {
             // wide hidden layer with enough environments per genome: tensor cores (3xTF32, tcgen05 + TMEM)

@@ -225,12 +225,16 @@ int ngp_evaluate_stepwise(ngp_handle *h, const RolloutParams &p, cudaStream_t st
     }
     NGP_CUDA(cudaGetLastError());
     const int per_genome = rr ? 2 * p.games : p.games;
+    {   // the population's networks are built once per evaluation (main.py:29) and run every frame
+        const int rc = ngp_mlp_prepare(h, p.genomes, p.n, st);
+        if (rc != NGP_OK) return rc;
+    }
     for (long long frame = 1;; ++frame) {
         if (p.core) step_frame_kernel<1><<<(total + 31) / 32, 32, 0, st>>>(p, envs, total, x, x_hof);
         else step_frame_kernel<0><<<(total + 31) / 32, 32, 0, st>>>(p, envs, total, x, x_hof);
         h->launches++;
         NGP_CUDA(cudaGetLastError());
-        int rc = ngp_mlp_forward(h, p.genomes, x, p.n, per_genome, act, nullptr, st);
+        int rc = ngp_mlp_forward_prepared(h, p.genomes, x, p.n, per_genome, act, nullptr, st);
         if (rc != NGP_OK) return rc;
         if (hof) {
             rc = ngp_mlp_forward(h, h->step_opp, x_hof, (int32_t)rows_hof, 1, act_hof, nullptr, st);

@@ -131,6 +131,23 @@ class Engine:
         _lib.check(self._L.ngp_mlp_forward(self._h, _p(genomes), _p(x), n, envs, _p(act), _p(out), _stream(self.device)), "ngp_mlp_forward")
         return act, out
 
+    def mlp_prepare(self, genomes: torch.Tensor):
+        """NeuralNetwork.__init__/populate_weights for a whole genome set: packs the wide layers once (ngp_mlp_prepare)."""
+        self._check_tensor(genomes, torch.float32, "genomes")
+        assert genomes.shape[1] == self.gene_size
+        _lib.check(self._L.ngp_mlp_prepare(self._h, _p(genomes), genomes.shape[0], _stream(self.device)), "ngp_mlp_prepare")
+
+    def mlp_forward_prepared(self, genomes: torch.Tensor, x: torch.Tensor, want_out: bool = True):
+        """mlp_forward on the genome set last passed to mlp_prepare (weights streamed from the packed copy)."""
+        self._check_tensor(genomes, torch.float32, "genomes")
+        self._check_tensor(x, torch.float32, "x")
+        n, envs = x.shape[0], x.shape[1]
+        act = torch.empty((n, envs), dtype=torch.uint8, device=self.device)
+        out = torch.empty((n, envs, self.config.NETWORK_SHAPE[-1]), dtype=torch.float32, device=self.device) if want_out else None
+        _lib.check(self._L.ngp_mlp_forward_prepared(self._h, _p(genomes), _p(x), n, envs, _p(act), _p(out), _stream(self.device)),
+                   "ngp_mlp_forward_prepared")
+        return act, out
+
     # ---- fused hot path ----------------------------------------------------------------------
     def evaluate(self, genomes: torch.Tensor, hof_genomes: torch.Tensor | None = None, hof_fitness: torch.Tensor | None = None,
                  hof_pick: torch.Tensor | None = None, seed: int = 0, generation: int = 0, want_detail: bool = False,

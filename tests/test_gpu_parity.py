@@ -323,7 +323,8 @@ def test_env_step_fast_flavour_equals_verify_flavour(ngp):
             assert torch.equal(outs[0][f][2], outs[k][f][2]) and torch.equal(outs[0][f][1], outs[k][f][1]), f"observation frame {f}"
 
 
-@pytest.mark.parametrize("nodes,envs", [((6, 512, 512, 2), 64), ((6, 512, 512, 2), 40), ((6, 128, 192, 2), 64), ((6, 64, 64, 64, 2), 17)])
+@pytest.mark.parametrize("nodes,envs", [((6, 512, 512, 2), 64), ((6, 512, 512, 2), 40), ((6, 128, 192, 2), 64), ((6, 64, 64, 64, 2), 17),
+                                        ((6, 512, 512, 2), 128), ((6, 200, 72, 2), 100), ((6, 512, 512, 512, 2), 130)])
 def test_mlp_forward_tensor_core_path(ngp, nodes, envs):
     """Wide hidden layers with >= 16 environments per genome run on tcgen05 (3xTF32, TMEM accumulators).  Tolerance:
     rtol 1e-5 against the FP64 oracle (the north_star's FP32 bar; plain TF32 would be ~1e-3), argmax 100 %; the
@@ -348,6 +349,16 @@ def test_mlp_forward_tensor_core_path(ngp, nodes, envs):
     np.testing.assert_allclose(out.cpu().numpy(), ref_out, rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(out_f.cpu().numpy(), ref_out, rtol=1e-5, atol=1e-7)
     assert np.array_equal(act.cpu().numpy(), ref_act) and np.array_equal(act_f.cpu().numpy(), ref_act)
+    # prepared genome set (ngp_mlp_prepare + ngp_mlp_forward_prepared): weights streamed from the packed copy into tensor memory
+    gd = torch.from_numpy(genomes).cuda()
+    eng.mlp_prepare(gd)
+    act_p, out_p = eng.mlp_forward_prepared(gd, torch.from_numpy(x).cuda())
+    np.testing.assert_allclose(out_p.cpu().numpy(), ref_out, rtol=1e-5, atol=1e-7)
+    assert np.array_equal(act_p.cpu().numpy(), ref_act)
+    act_p2, out_p2 = eng.mlp_forward_prepared(gd, torch.from_numpy(x).cuda())
+    assert torch.equal(out_p, out_p2) and torch.equal(act_p, act_p2)
+    with pytest.raises(ngp.NgpError):                   # another genome set was not prepared
+        eng.mlp_forward_prepared(gd.clone(), torch.from_numpy(x).cuda())
     eng.close()
 
 

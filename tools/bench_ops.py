@@ -70,17 +70,20 @@ def main():
     # K3 wide net, 64 envs per genome: weights streamed once per genome
     engw = ngp.Engine(ngp.Config(NETWORK_SHAPE=(6, 512, 512, 2)), device=0)
     G = engw.gene_size
+    envs_w = int(sys.argv[sys.argv.index("--envs") + 1]) if "--envs" in sys.argv else 64
     for n in (64, 256, 1024) if "mlp_wide" in only else ():
         g = (torch.randn((n, G), device="cuda") * 0.05)
-        x = torch.rand((n, 64, 6), device="cuda")
-        for path in ("tcgen05_3xtf32", "fp32_ffma"):
+        x = torch.rand((n, envs_w, 6), device="cuda")
+        engw.mlp_prepare(g)
+        for path in ("prepared_tmem_3xtf32", "tcgen05_3xtf32", "fp32_ffma"):
             if path == "fp32_ffma":
-                os.environ["NGP_MLP_NO_TF32"] = "1"
-            t = timed(lambda: engw.mlp_forward(g, x, want_out=False), iters=5, warm=2)
-            os.environ.pop("NGP_MLP_NO_TF32", None)
-            flops = 2.0 * G * 64 * n
-            print(json.dumps({"op": "mlp_forward[6,512,512,2]", "path": path, "config": {"genomes": n, "envs": 64}, "ms": t * 1e3,
-                              "inferences_per_s": n * 64 / t, "algorithmic_gbs": n * G * 4 / t / 1e9, "hbm_peak_gbs": PEAK,
+                engw.set_option("mlp_no_tf32", 1)
+            fn = (lambda: engw.mlp_forward_prepared(g, x, want_out=False)) if path.startswith("prepared") else (lambda: engw.mlp_forward(g, x, want_out=False))
+            t = timed(fn, iters=5, warm=2)
+            engw.set_option("mlp_no_tf32", 0)
+            flops = 2.0 * G * envs_w * n
+            print(json.dumps({"op": "mlp_forward[6,512,512,2]", "path": path, "config": {"genomes": n, "envs": envs_w}, "ms": t * 1e3,
+                              "inferences_per_s": n * envs_w / t, "algorithmic_gbs": n * G * 4 / t / 1e9, "hbm_peak_gbs": PEAK,
                               "frac": n * G * 4 / t / 1e9 / PEAK, "tflops_algorithmic": flops / t / 1e12}), flush=True)
     engw.close()
     # K4: GA step, ~3*N*G*4 bytes
