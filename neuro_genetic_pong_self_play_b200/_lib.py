@@ -62,7 +62,8 @@ def load(build_if_missing: bool = True):
         if not build_if_missing:
             raise NgpError(f"{_build.LIB_PATH} is missing and there is no CPU fallback; run __graft_entry__.build()")
         _build.build()
-    L = ctypes.CDLL(_build.LIB_PATH)
+    # NGP_LIBRARY: another build of the same sources (kernel experiments: tools/ variants); the default is the in-tree library
+    L = ctypes.CDLL(os.environ.get("NGP_LIBRARY") or _build.LIB_PATH)
     vp, i32, u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64
     L.ngp_config_size.restype = i32
     if L.ngp_config_size() != ctypes.sizeof(NgpConfig):

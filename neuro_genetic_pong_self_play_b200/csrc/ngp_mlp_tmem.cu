@@ -8,10 +8,12 @@
 //
 //   ngp_mlp_prepare   packs every wide layer of every genome into 128-output x 16-k tiles  [tile][q][row][4 floats]  (one
 //                     coalesced 16-byte load per thread and quarter-chunk) and the bias weights into their own vector
-//   A producers       4 warps, thread = output row (= TMEM lane): LDG.128 x 4 per chunk, PF chunks ahead in registers,
-//                     split  w = hi + lo  (hi = tf32-truncated), tcgen05.st hi and lo into a 4-stage ring of TMEM columns
-//   B producers       4 warps: activations [env][k] (L2-resident, 16-byte aligned rows) -> registers -> hi/lo tiles in shared
-//                     memory in the canonical no-swizzle K-major core-matrix layout (the only shared-memory traffic left)
+//   copy warp         one thread: each 128 x 16 tile is 8 KB of CONTIGUOUS packed memory -> one cp.async.bulk (TMA, 1-D) per chunk
+//                     into a deep ring of raw tiles in shared memory (up to 64 KB in flight per CTA, no registers held)
+//   A producers       4 warps, thread = output row (= TMEM lane): 4 x LDS.128 of its row (conflict-free), split  w = hi + lo
+//                     (hi = tf32-truncated), tcgen05.st hi and lo into a 4-stage ring of TMEM columns
+//   B producers       4 warps, warp w owns stage w: activations [env][k] (L2-resident, 16-byte aligned rows) -> registers ->
+//                     hi/lo tiles in shared memory in the canonical no-swizzle K-major core-matrix layout
 //   MMA warp          per chunk and k-step of 8:  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  ("3xTF32", error ~2^-21) with A from
 //                     TMEM and B from shared memory; tcgen05.commit hands the stage back to both producer groups
 //   epilogue          the A producers (their warp owns the TMEM lanes of its rows): tcgen05.ld, + bias, sigmoid, coalesced stores
@@ -19,19 +21,22 @@
 // D^T form as before: M = 128 outputs, N = TN environments (64 or 128: with 128 a genome's weights are streamed once for the
 // 2 x 64 rows of the round-robin stepwise evaluation), K = fan-in (bias handled in the epilogue, so K = 512 exactly for the
 // flagship net).  TMEM: TN accumulator columns + 4 stages x (16 hi + 16 lo) columns = 256 -> two CTAs per SM.
+// Shared-memory traffic per weight byte: one bulk write + one read (2 B/B) instead of ~10 B/B; the tensor core reads only B.
 #include "ngp_internal.h"
 
 namespace tmm {
 
-constexpr int TM = 128, KC = 16, STAGES = 4, PF = 3;
+constexpr int TM = 128, KC = 16, STAGES = 4;
 constexpr uint32_t SBO = 128;
 constexpr uint32_t TMEM_COLS = 256;
-constexpr int A_THREADS = 128, B_THREADS = 128, THREADS = A_THREADS + B_THREADS + 32;
+constexpr int A_THREADS = 256, B_THREADS = 128, THREADS = A_THREADS + B_THREADS + 64;      // + MMA warp + copy warp
+constexpr uint32_t RAW_TILE = KC * TM * 4;                                                 // 8 KB: one packed 128 x 16 weight tile
 
 __host__ __device__ constexpr uint32_t lbo(int TN) { return (uint32_t)TN * 16u + 16u; }            // +16 B: conflict-free stores
 __host__ __device__ constexpr uint32_t tile_b(int TN) { return (KC / 4) * lbo(TN); }               // one of B_hi / B_lo
 __host__ __device__ constexpr uint32_t stage_b(int TN) { return 2 * tile_b(TN); }
-__host__ __device__ constexpr uint32_t smem_bytes(int TN) { return STAGES * stage_b(TN) + 128; }
+__host__ __device__ constexpr int raw_stages(int TN) { return TN > 64 ? 5 : 8; }           // two CTAs per SM must fit 227 KB
+__host__ __device__ constexpr uint32_t smem_bytes(int TN) { return STAGES * stage_b(TN) + raw_stages(TN) * RAW_TILE + 256 + 128; }
 __host__ __device__ constexpr uint32_t idesc(int TN)
 {
     // cute::UMMA::InstrDescriptor: D=F32 (bit 4), A=B=TF32 (2 at bits 7, 10), both K-major, N>>3 at 17, M>>4 at 24
@@ -73,11 +78,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
                    "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
-__device__ __forceinline__ float4 ldg_stream(const float4 *p)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t tf32_hi(float v) { return __float_as_uint(v) & 0xFFFFE000u; }
 
@@ -123,22 +132,25 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
                       float *__restrict__ out)
 {
     constexpr uint32_t LBO = lbo(TN), TILE_B = tile_b(TN), STAGE_B = stage_b(TN), IDESC = idesc(TN);
-    constexpr int B_UNITS = TN * (KC / 4) / B_THREADS;                   // 16-byte units of a B chunk per producer thread (4 or 2)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.z, e0 = blockIdx.y * TN, ob = blockIdx.x;
     const int NC = (ni + KC - 1) / KC;
     const uint32_t smem_base = smem_u32(smem);
-    // barriers: a_full[s] (4 warps), b_full[s] (4 warps), free[s] (one commit), done
-    const uint32_t bar_a = smem_base + STAGES * STAGE_B, bar_b = bar_a + 8 * STAGES, bar_free = bar_b + 8 * STAGES, bar_done = bar_free + 8 * STAGES;
+    constexpr int NA = raw_stages(TN);
+    const uint32_t raw_base = smem_base + STAGES * STAGE_B;               // NA raw weight tiles (bulk-copy destinations, 128-byte aligned)
+    // barriers: a_full[s] (4 warps), b_full[s] (4 warps), free[s] (one commit), raw_full[r] (copy thread + bytes), raw_free[r] (4 warps), done
+    const uint32_t bar_a = raw_base + NA * RAW_TILE, bar_b = bar_a + 8 * STAGES, bar_free = bar_b + 8 * STAGES, bar_done = bar_free + 8 * STAGES;
+    const uint32_t bar_rfull = bar_done + 8, bar_rfree = bar_rfull + 8 * NA;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_a + 8 * s, A_THREADS / 32); mbar_init(bar_b + 8 * s, B_THREADS / 32); mbar_init(bar_free + 8 * s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_a + 8 * s, 4); mbar_init(bar_b + 8 * s, 1); mbar_init(bar_free + 8 * s, 1); }
+        for (int r = 0; r < NA; ++r) { mbar_init(bar_rfull + 8 * r, 1); mbar_init(bar_rfree + 8 * r, 4); }
         mbar_init(bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -147,93 +159,97 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_slot;                              // columns [0, TN): accumulator
     const uint32_t tmem_a = tmem_d + 128;                                // columns [128, 256): 4 stages x (16 hi + 16 lo)
+    const float *tiles = packed + (size_t)g * per_genome + layer_off + (size_t)ob * NC * (KC * TM);       // this CTA's NC contiguous 8 KB tiles
 
-    if (warp < A_THREADS / 32) {
-        // ------------------------------- A producers: thread = output row = TMEM lane -------------------------------
-        const float4 *src = reinterpret_cast<const float4 *>(packed + (size_t)g * per_genome + layer_off) + (size_t)ob * NC * (4 * TM) + tid;
-        float4 pre[PF][4];
-#pragma unroll
-        for (int p = 0; p < PF; ++p)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) pre[p][q] = p < NC ? ldg_stream(src + ((size_t)p * 4 + q) * TM) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const uint32_t lane_addr = tmem_a + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < NC; c0 += PF) {
-#pragma unroll
-            for (int p = 0; p < PF; ++p) {
-                const int c = c0 + p;
-                if (c < NC) {
-                    const int s = c % STAGES;
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 v = pre[p][q];
-                        hi[4 * q + 0] = tf32_hi(v.x); lo[4 * q + 0] = __float_as_uint(v.x - __uint_as_float(hi[4 * q + 0]));
-                        hi[4 * q + 1] = tf32_hi(v.y); lo[4 * q + 1] = __float_as_uint(v.y - __uint_as_float(hi[4 * q + 1]));
-                        hi[4 * q + 2] = tf32_hi(v.z); lo[4 * q + 2] = __float_as_uint(v.z - __uint_as_float(hi[4 * q + 2]));
-                        hi[4 * q + 3] = tf32_hi(v.w); lo[4 * q + 3] = __float_as_uint(v.w - __uint_as_float(hi[4 * q + 3]));
-                    }
-                    const int cn = c + PF;                               // refill the register slot
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) if (cn < NC) pre[p][q] = ldg_stream(src + ((size_t)cn * 4 + q) * TM);
-                    if (c >= STAGES) {                                   // the MMAs that read this stage STAGES chunks ago are done
-                        mbar_wait(bar_free + 8 * s, ((c / STAGES) - 1) & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    }
-                    tmem_st16(lane_addr + (uint32_t)(s * 32), hi);
-                    tmem_st16(lane_addr + (uint32_t)(s * 32 + 16), lo);
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_a + 8 * s);
-                }
+    if (warp == (A_THREADS + B_THREADS) / 32 + 1) {
+        // ------------------------------- copy warp: one bulk copy per chunk, NA chunks ahead -------------------------------
+        if (lane == 0) {
+            for (int c = 0; c < NC; ++c) {
+                const int r = c % NA;
+                if (c >= NA) mbar_wait(bar_rfree + 8 * r, ((c / NA) - 1) & 1);
+                mbar_expect_tx(bar_rfull + 8 * r, RAW_TILE);
+                bulk_g2s(raw_base + r * RAW_TILE, tiles + (size_t)c * (KC * TM), RAW_TILE, bar_rfull + 8 * r);
             }
         }
-    } else if (warp < (A_THREADS + B_THREADS) / 32) {
-        // ------------------------------- B producers: activations -> hi/lo tiles in shared memory -------------------------------
-        const int t = tid - A_THREADS;
-        const int cu = t & 3, r0 = t >> 2;                               // k-unit of the chunk, first row; rows r0 + 32 j
-        const float *A = in + (size_t)g * envs * ni;
-        float4 pre[PF][B_UNITS];
-        auto fetch = [&](int c, float4 (&dst)[B_UNITS]) {
-#pragma unroll
-            for (int j = 0; j < B_UNITS; ++j) {
-                const int row = e0 + r0 + 32 * j, k = c * KC + cu * 4;
-                dst[j] = (c < NC && row < envs && k < ni) ? __ldg(reinterpret_cast<const float4 *>(A + (size_t)row * ni + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+    } else if (warp < A_THREADS / 32) {
+        // ------------------------------- A producers: thread = output row = TMEM lane -------------------------------
+        // Eight warps: warp w serves TMEM lane quadrant w & 3 (the lanes a warp may access) and the chunks of parity w >> 2.
+        // The completion of a chunk's tcgen05.st is only awaited after the next chunk of this warp has been loaded and split.
+        const int quad = warp & 3, par = warp >> 2, row = quad * 32 + lane;
+        const uint32_t lane_addr = tmem_a + ((uint32_t)(quad * 32) << 16);
+        int pending = -1;                                                // chunk whose stores have been issued but not yet published
+        auto publish = [&](int c) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_a + 8 * (c % STAGES));
+                mbar_arrive(bar_rfree + 8 * (c % NA));                   // every lane's loads of the raw tile have been consumed by its stores
             }
         };
-#pragma unroll
-        for (int p = 0; p < PF; ++p) fetch(p, pre[p]);
 #pragma unroll 1
-        for (int c0 = 0; c0 < NC; c0 += PF) {
+        for (int c = par; c < NC; c += 2) {
+            const int r = c % NA, s = c % STAGES;
+            mbar_wait(bar_rfull + 8 * r, (c / NA) & 1);
+            const float4 *raw = reinterpret_cast<const float4 *>(smem + STAGES * STAGE_B + r * RAW_TILE) + row;       // [q][row] float4
+            uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int p = 0; p < PF; ++p) {
-                const int c = c0 + p;
-                if (c < NC) {
-                    const int s = c % STAGES;
-                    if (c >= STAGES) mbar_wait(bar_free + 8 * s, ((c / STAGES) - 1) & 1);
-                    uint8_t *stage = smem + s * STAGE_B;
-#pragma unroll
-                    for (int j = 0; j < B_UNITS; ++j) {
-                        const int r = r0 + 32 * j;
-                        const float4 v = pre[p][j];
-                        float4 h, l;
-                        h.x = __uint_as_float(tf32_hi(v.x)); l.x = v.x - h.x;
-                        h.y = __uint_as_float(tf32_hi(v.y)); l.y = v.y - h.y;
-                        h.z = __uint_as_float(tf32_hi(v.z)); l.z = v.z - h.z;
-                        h.w = __uint_as_float(tf32_hi(v.w)); l.w = v.w - h.w;
-                        uint8_t *dst = stage + cu * LBO + (r >> 3) * SBO + (r & 7) * 16;
-                        *reinterpret_cast<float4 *>(dst) = h;
-                        *reinterpret_cast<float4 *>(dst + TILE_B) = l;
-                    }
-                    fetch(c + PF, pre[p]);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_b + 8 * s);
-                }
+            for (int q = 0; q < 4; ++q) {
+                const float4 v = raw[q * TM];
+                hi[4 * q + 0] = tf32_hi(v.x); lo[4 * q + 0] = __float_as_uint(v.x - __uint_as_float(hi[4 * q + 0]));
+                hi[4 * q + 1] = tf32_hi(v.y); lo[4 * q + 1] = __float_as_uint(v.y - __uint_as_float(hi[4 * q + 1]));
+                hi[4 * q + 2] = tf32_hi(v.z); lo[4 * q + 2] = __float_as_uint(v.z - __uint_as_float(hi[4 * q + 2]));
+                hi[4 * q + 3] = tf32_hi(v.w); lo[4 * q + 3] = __float_as_uint(v.w - __uint_as_float(hi[4 * q + 3]));
             }
+            if (pending >= 0) publish(pending);
+            if (c >= STAGES) {                                           // the MMAs that read this TMEM stage STAGES chunks ago are done
+                mbar_wait(bar_free + 8 * s, ((c / STAGES) - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            tmem_st16(lane_addr + (uint32_t)(s * 32), hi);
+            tmem_st16(lane_addr + (uint32_t)(s * 32 + 16), lo);
+            pending = c;
         }
-    } else {
+        if (pending >= 0) publish(pending);
+    } else if (warp < (A_THREADS + B_THREADS) / 32) {
+        // ------------------------------- B producers: activations -> hi/lo tiles in shared memory -------------------------------
+        // Warp w fills stage w: chunks w, w + 4, ...  A warp loads a whole chunk (TN rows x 64 bytes), waits for it, splits and
+        // stores it, and only then fences: fence.proxy.async compiles to a MEMBAR that also waits for the thread's outstanding
+        // global loads, so nothing may be in flight across it; the latency is hidden by the other three warps' chunks instead.
+        const int wb = warp - A_THREADS / 32;
+        constexpr int UNITS = TN * (KC / 4) / 32;                        // 16-byte units per lane and chunk (8 or 16)
+        const float *A = in + (size_t)g * envs * ni;
+        // unit u = lane + 32 j: 8 consecutive lanes = 8 consecutive rows of one k-unit (conflict-free 128-byte store rows);
+        // k-unit = (lane >> 3) & 3, row = (lane & 7) + 8 j
+        const int cu = (lane >> 3) & 3, rl = lane & 7;
+#pragma unroll 1
+        for (int c = wb; c < NC; c += STAGES) {
+            float4 v[UNITS];
+#pragma unroll
+            for (int j = 0; j < UNITS; ++j) {
+                const int row = e0 + rl + 8 * j, k = c * KC + cu * 4;
+                v[j] = (row < envs && k < ni) ? __ldg(reinterpret_cast<const float4 *>(A + (size_t)row * ni + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (c >= STAGES) mbar_wait(bar_free + 8 * wb, ((c / STAGES) - 1) & 1);
+            uint8_t *stage = smem + wb * STAGE_B;
+#pragma unroll
+            for (int j = 0; j < UNITS; ++j) {
+                const int r = rl + 8 * j;
+                float4 h, l;
+                h.x = __uint_as_float(tf32_hi(v[j].x)); l.x = v[j].x - h.x;
+                h.y = __uint_as_float(tf32_hi(v[j].y)); l.y = v[j].y - h.y;
+                h.z = __uint_as_float(tf32_hi(v[j].z)); l.z = v[j].z - h.z;
+                h.w = __uint_as_float(tf32_hi(v[j].w)); l.w = v[j].w - h.w;
+                uint8_t *dst = stage + cu * LBO + (r >> 3) * SBO + (r & 7) * 16;
+                *reinterpret_cast<float4 *>(dst) = h;
+                *reinterpret_cast<float4 *>(dst + TILE_B) = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_b + 8 * wb);
+        }
+    } else if (warp == (A_THREADS + B_THREADS) / 32) {
         // ------------------------------- MMA warp -------------------------------
         if (lane == 0) {
             for (int c = 0; c < NC; ++c) {
@@ -257,16 +273,18 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
         }
         __syncwarp();
     }
-    // ------------------------------- epilogue: the A producers own the TMEM lanes of their rows -------------------------------
+    // ------------------------------- epilogue: the A producers (warp w: lane quadrant w & 3, column half w >> 2) -------------------------------
     if (warp < A_THREADS / 32) {
         mbar_wait(bar_done, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int o = ob * TM + tid;
+        const int quad = warp & 3, colh = warp >> 2;
+        const int o = ob * TM + quad * 32 + lane;
         const float b = packed[(size_t)g * per_genome + layer_off + (size_t)((no + TM - 1) / TM) * NC * (KC * TM) + o];
 #pragma unroll 1
-        for (int half = 0; half < TN / 32; ++half) {
+        for (int part = 0; part < TN / 64; ++part) {
+            const int col0 = colh * (TN / 2) + part * 32;
             uint32_t v[32];
-            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(half * 32);
+            const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -278,11 +296,12 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
                 : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (o < no) {
-                float *dst = out + ((size_t)g * envs + e0 + half * 32) * no + o;
-                const int e_left = envs - (e0 + half * 32);
+                float *dst = out + ((size_t)g * envs + e0 + col0) * no + o;
+                const int e_left = envs - (e0 + col0);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    if (j < e_left) *dst = __frcp_rn(1.0f + __expf(-(__uint_as_float(v[j]) + b)));
+                    // fast exponential and reciprocal (ex2.approx, rcp.approx: a few ulp), far inside the 1e-5 bar
+                    if (j < e_left) *dst = __fdividef(1.0f, 1.0f + __expf(-(__uint_as_float(v[j]) + b)));
                     dst += no;
                 }
             }
