@@ -262,8 +262,8 @@ def run_generations(toolbox: Toolbox, genomes: torch.Tensor, ngen: int, fitness:
 
 # ---- checkpoint / resume (utils.py:116-125, ga.py:13-53) -------------------------------------------
 # Layout: one .npz per checkpoint (population, fitness, hall of fame, Philox seed + generation counter = the RNG state,
-# network_shape, bias).  The reference pickles DEAP objects (deap.creator.Individual, tools.HallOfFame) that cannot be
-# unpickled without DEAP; those files are NOT read here (a warning is printed when only such files are present).
+# network_shape, bias).  The reference pickles DEAP objects (deap.creator.Individual, tools.HallOfFame); its files are read
+# one way by read_reference_checkpoint (stand-in classes, no DEAP needed), so a run of the reference can be continued here.
 def save_checkpoint(toolbox: Toolbox, genomes: torch.Tensor, fitness: torch.Tensor, directory: str = "checkpoints/checkpoints") -> str:
     os.makedirs(directory, exist_ok=True)
     path = os.path.join(directory, "c_{}.npz".format(time.strftime("%H_%M_%S")))
@@ -280,19 +280,72 @@ def save_checkpoint(toolbox: Toolbox, genomes: torch.Tensor, fitness: torch.Tens
     return path
 
 
+def read_reference_checkpoint(path: str):
+    """One-way importer of the REFERENCE's checkpoints (utils.save_checkpoint, utils.py:116-125: a pickled dict with
+    population = list of deap.creator.Individual, hall_of_fame = deap.tools.HallOfFame, rndstate, network_shape) without
+    DEAP: the unpickler substitutes plain stand-ins for every class under `deap.` (an Individual is a list of genes whose
+    `fitness.wvalues` holds the weighted fitness; weights are (1.0,), ga.py:80).  Returns a dict with population f32[N][G],
+    fitness f64[N] (NaN = invalid), hof_genomes, hof_fitness (best first), network_shape.  `rndstate` (Python's Mersenne
+    twister) has no counterpart here: the Philox seed/generation of the toolbox stay as they are."""
+    import pickle
+
+    class _Obj:
+        def __setstate__(self, state):
+            if isinstance(state, tuple) and len(state) == 2 and isinstance(state[1], dict):      # (dict, slots)
+                state = {**(state[0] or {}), **state[1]}
+            self.__dict__.update(state or {})
+
+    class _Seq(list, _Obj):
+        pass
+
+    class _Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if module.split(".")[0] in ("deap", "scoop"):
+                return _Seq if name == "Individual" else type(name, (_Obj,), {})
+            return super().find_class(module, name)
+
+    with open(path, "rb") as f:
+        cp = _Unpickler(f).load()
+
+    def fit_of(ind):
+        w = getattr(getattr(ind, "fitness", None), "wvalues", ())
+        return float(w[0]) if len(w) else float("nan")
+
+    pop = list(cp["population"])
+    out = {"population": np.asarray([list(i) for i in pop], np.float32).reshape(len(pop), -1),
+           "fitness": np.asarray([fit_of(i) for i in pop], np.float64),
+           "network_shape": tuple(int(v) for v in cp.get("network_shape", ())) or None}
+    hof = cp.get("hall_of_fame")
+    items = list(getattr(hof, "items", [])) if hof is not None else []
+    out["hof_genomes"] = np.asarray([list(i) for i in items], np.float32).reshape(len(items), -1)
+    out["hof_fitness"] = np.asarray([fit_of(i) for i in items], np.float64)          # DEAP keeps items best first
+    return out
+
+
 def load_latest_population(toolbox: Toolbox, directory: str = "checkpoints/checkpoints"):
     """Newest checkpoint by ctime (ga.py:32-38), sorted by fitness descending (ga.py:45), truncated or topped up with fresh
     random individuals to POPULATION_SIZE (ga.py:13-29).  Returns (genomes, fitness); fitness is None without a checkpoint
     and holds NaN for topped-up (never evaluated) individuals -- loaded individuals keep their fitness, as in the reference."""
-    files = glob.glob(os.path.join(directory, "*.npz"))
+    files = glob.glob(os.path.join(directory, "*.npz")) + glob.glob(os.path.join(directory, "*.pkl"))
     n = toolbox.config.POPULATION_SIZE
     if not files:
         others = glob.glob(os.path.join(directory, "*"))
         if others:
-            warnings.warn(f"{len(others)} file(s) in {directory} are not .npz checkpoints of this package (the reference's "
-                          "pickles need DEAP to load) and are ignored")
+            warnings.warn(f"{len(others)} file(s) in {directory} are neither .npz checkpoints of this package nor the reference's "
+                          ".pkl checkpoints and are ignored")
         return toolbox.population(n), None
-    cp = np.load(max(files, key=os.path.getctime))
+    newest = max(files, key=os.path.getctime)
+    if newest.endswith(".pkl"):                          # a checkpoint written by the reference itself (utils.py:116-125)
+        ref = read_reference_checkpoint(newest)
+        if ref["population"].shape[1] != toolbox.engine.gene_size:
+            raise _lib.NgpError("reference checkpoint gene size differs from the configured NETWORK_SHAPE; rebuild the Toolbox with it")
+        valid = ~np.isnan(ref["hof_fitness"])            # utils.py:96-98 skips hall-of-fame members without a valid fitness
+        cp = {"network_shape": np.asarray(ref["network_shape"] or toolbox.config.NETWORK_SHAPE, np.int32), "fitness": ref["fitness"],
+              "population": ref["population"], "seed": toolbox.seed, "generation": toolbox.generation,
+              "hof_genomes": ref["hof_genomes"][valid], "hof_fitness": ref["hof_fitness"][valid]}
+        cp["fitness"] = np.where(np.isnan(cp["fitness"]), -np.inf, cp["fitness"])            # invalid individuals sort last ...
+    else:
+        cp = np.load(newest)
     if tuple(int(v) for v in cp["network_shape"]) != tuple(toolbox.config.NETWORK_SHAPE):
         raise _lib.NgpError("checkpoint network_shape differs from the configured NETWORK_SHAPE; rebuild the Toolbox with it")
     if "bias" in cp and bool(int(cp["bias"])) != bool(toolbox.config.BIAS):
@@ -302,6 +355,7 @@ def load_latest_population(toolbox: Toolbox, directory: str = "checkpoints/check
     toolbox.seed = int(cp["seed"]); toolbox.generation = int(cp["generation"])
     toolbox.hall_of_fame.load(cp["hof_genomes"], cp["hof_fitness"])
     dev = toolbox.engine.device
+    fit = np.where(np.isinf(fit), np.nan, fit)                                                # ... and are re-evaluated
     genomes = torch.from_numpy(np.ascontiguousarray(pop)).to(dev)
     fitness = torch.from_numpy(np.ascontiguousarray(fit)).to(dev)
     if len(pop) < n:

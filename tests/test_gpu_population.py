@@ -354,6 +354,29 @@ def test_checkpoint_round_trip_truncate_and_top_up(ngp, tmp_path):
         e.close()
 
 
+def test_resume_from_a_reference_checkpoint(ngp, tmp_path):
+    """load_latest_population continues from a checkpoint the REFERENCE wrote (pickled DEAP objects, utils.py:116-125): sorted by
+    fitness, invalid individuals re-evaluated, hall of fame restored without its invalid members (utils.py:96-98), topped up."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_reference_checkpoint import _write_reference_style_checkpoint
+    from neuro_genetic_pong_self_play_b200.reference_api import Toolbox, load_latest_population
+    cfg = ngp.Config(POPULATION_SIZE=8)
+    tb = Toolbox(cfg, ngp.Engine(cfg, device=0), seed=5)
+    rng = np.random.RandomState(3)
+    genes = rng.standard_normal((6, tb.engine.gene_size)).astype(np.float32)
+    fits = np.array([0.25, np.nan, 1.5, -0.5, 0.75, 0.0])
+    _write_reference_style_checkpoint(tmp_path / "c_01_02_03.pkl", genes, fits, hof_idx=[2, 4, 1])
+    genomes, fitness = load_latest_population(tb, str(tmp_path))
+    g, f = genomes.cpu().numpy(), fitness.cpu().numpy()
+    assert g.shape == (8, tb.engine.gene_size)
+    assert np.array_equal(g[:5], genes[[2, 4, 0, 5, 3]]) and f[:5].tolist() == [1.5, 0.75, 0.25, 0.0, -0.5]
+    assert np.array_equal(g[5], genes[1]) and np.isnan(f[5:]).all()          # the invalid individual and the two fresh ones
+    hg, hf = tb.hall_of_fame.tensors()
+    assert hf.cpu().tolist() == [1.5, 0.75] and np.array_equal(hg.cpu().numpy(), genes[[2, 4]])
+    tb.engine.close()
+
+
 def test_reference_call_surface(ngp, golden, obs_npy):
     """NeuralNetwork(nodes, weights, bias).run, find_stuff(obs), toolbox.evaluate(individual), toolbox.map(toolbox.evaluate, pop)
     read like the reference's call sites (numpy_nn.py:35-50,120-137; utils.py:14-19; main.py:28-66; ga.py:83)."""
