@@ -489,7 +489,27 @@ def main():
             return {"workload": w["name"], "env_frames_per_s": f / (m * 1e-3), "ms_per_step": m / steps, "rollout_ms_per_step": r / steps,
                     "frames_per_step": f / steps, "steps": steps, "warmup": warmup, "scaling": w["scaling"]}
 
+        def lockstep():
+            """Throughput capability of the fused kernel with every lane busy: 32 768 genomes per GPU (196 608 environments), every
+            episode capped at 300 frames (MAX_FRAMES), so no lane waits for a marathon rally.  NOT the GA workload (episodes are
+            cut short): context for north_star's >= 1e9 frames/s target."""
+            n2 = 32768
+            cfg2 = ngp.Config(SCHEDULE=ngp.SCHEDULE_ROUND_ROBIN, POPULATION_SIZE=n2, GAMES_TO_PLAY=GAMES, MAX_FRAMES=300)
+            e2 = ngp.Engine(cfg2, device=local)
+            g2 = e2.init_population(n2, seed=SEED_POP + rank)
+            e2.evaluate(g2, seed=5)
+            e2.profile_enable(True); e2.profile_read()
+            total = 0
+            for rep in range(2):
+                total += e2.evaluate(g2, seed=6 + rep)["frames_total"]
+            ms2, _ = e2.profile_read()
+            e2.close()
+            (ms2,), (total,) = reduce_ranks(torch, dist, world, [ms2], [float(total)])
+            return {"workload": f"{n2} genomes/GPU round-robin, {n2 * GAMES} envs/GPU, episodes capped at 300 frames (lock-step regime, not the GA workload)",
+                    "env_frames_per_s": total / (ms2 * 1e-3), "kernel_ms": ms2 / 2, "n_gpus": world}
+
         for name, fn in (("config1", lambda: short(1, 3, 1)),
+                         ("lockstep_capability", lockstep),
                          ("config3", lambda: short(3, 2, 1)),
                          ("config4", lambda: short(4, 1, 1)),
                          ("config5", lambda: config5_sweep(ngp, local, world, D))):
