@@ -8,6 +8,7 @@ Names and argument meaning follow the reference so its call sites read the same:
   HallOfFame(maxsize).update(population)                       ga.py:78 (DEAP tools.HallOfFame)
   run_generations(...)  (eaSimple-shaped loop + logbook)       main.py:157-173
   save_checkpoint / load_latest_population                     utils.py:116-125, ga.py:13-53
+  replay(individual) / repeat_upsample                         pickle_inspector.py:1-12, main.py:115-125, utils.py:156-168
 Every call lands in libngp.so's CUDA kernels through Engine; nothing here computes on the CPU except argument
 marshalling (individuals are rows of device tensors instead of Python lists)."""
 from __future__ import annotations
@@ -258,6 +259,87 @@ def run_generations(toolbox: Toolbox, genomes: torch.Tensor, ngen: int, fitness:
     if sharded:
         consume()
     return genomes, fitness, log
+
+
+# ---- replay of one individual with frames (pickle_inspector.py:1-12 -> main.evaluate(individual, render=True), main.py:115-125) ----
+def repeat_upsample(rgb: torch.Tensor, k: int = 1, l: int = 1) -> torch.Tensor:
+    """utils.repeat_upsample (utils.py:156-168): every pixel repeated k times along y and l times along x; k or l <= 0 returns
+    the input unchanged (the reference logs an error once and does the same)."""
+    if k <= 0 or l <= 0:
+        return rgb
+    return rgb.repeat_interleave(k, dim=-3).repeat_interleave(l, dim=-2)
+
+
+def replay(toolbox: Toolbox, individual, game: int = 0, upsample=(4, 4), max_frames: int = 0):
+    """One game of main.evaluate's schedule for ONE individual, frame by frame through the explicit-action API (ngp_env_step),
+    keeping what the reference's viewer would show: returns dict(frames u8[T, 210*k, 160*l, 3] on the device -- render_game's
+    upscaled rgb_array per env.step --, reward, steps, score).  game: 0 HardcodedAi, 1 the cartridge robot (players=1),
+    2 ScoreHardcodedAi, 3..5 a hall-of-fame opponent when the toolbox has one (else HardcodedAi), as main.py:33-58.
+    The decisions use the same kernels as the batched path (ngp_mlp_forward for the networks); there is no window and no
+    sleeping to 60 fps -- showing the frames is the caller's business."""
+    eng, cfg = toolbox.engine, toolbox.config
+    dev = eng.device
+    g = (individual if isinstance(individual, torch.Tensor) else torch.tensor(np.asarray(individual, np.float32))).to(dev, torch.float32).reshape(1, -1).contiguous()
+    state = _lib.STATE_START_1P if game == 1 else _lib.STATE_START_2P
+    left_genome, mult, left_kind = None, 1.0, "score" if game == 2 else "hardcoded"
+    if game >= 3 and len(toolbox.hall_of_fame):
+        hg, hf = toolbox.hall_of_fame.tensors()
+        pick = int(torch.randint(len(toolbox.hall_of_fame), (1,)).item())
+        left_genome, mult, left_kind = hg[pick:pick + 1].contiguous(), float(hf[pick].item()), "mlp"
+    eng.env_reset(1, state)
+    action = torch.tensor([cfg.blank_action()], dtype=torch.uint8, device=dev)
+    frames, last_score, timeout, total, last_ball, steps = [], None, 0.0, 0.0, None, 0
+    W, H, PH = float(cfg.GAME_WIDTH), float(cfg.GAME_PLAYABLE_HEIGHT), cfg.SCALED_PADDLE_HEIGHT
+
+    def run(model, vec):
+        act, _ = eng.mlp_forward(model, torch.tensor([[vec]], dtype=torch.float32, device=dev), want_out=False)
+        return [1, 0] if int(act.item()) == _lib.ACT_UP else [0, 1]
+
+    def bot(vec, s1, s2):
+        if left_kind == "score" and s1 > s2:                           # dumb_ais.py:11-25
+            return [0, 0]
+        return [1, 0] if vec[1] < vec[4] else ([0, 1] if vec[1] > vec[4] else [0, 0])      # dumb_ais.py:1-8
+
+    def clamp(valid, row, act):                                       # utils.keep_within_game_bounds_please, utils.py:71-77
+        if valid:
+            if row < PH:
+                return [0, 1]
+            if row > H - PH:
+                return [1, 0]
+        return act
+
+    while True:
+        out = eng.env_step(action)
+        frames.append(repeat_upsample(out["frames"][0], *upsample))
+        ram = out["ram"][0].cpu().numpy()
+        s1, s2 = int(ram[13]), int(ram[14])
+        loc = out["loc"][0].double().cpu().numpy(); valid = out["valid"][0].cpu().numpy()
+        steps += 1
+        la, ra = [0, 0], [0, 0]
+        if valid[0]:                                                  # main.get_actions, main.py:138-154
+            ball = loc[0]; last = ball if last_ball is None else last_ball
+            if valid[1] and valid[2]:
+                rv = [ball[1] / W, ball[0] / H, last[1] / W, last[0] / H, loc[2][0] / H, loc[1][0] / H]
+                lv = [(W - ball[1]) / W, ball[0] / H, (W - last[1]) / W, last[0] / H, loc[1][0] / H, loc[2][0] / H]
+                ra = run(g, rv)
+                la = run(left_genome, lv) if left_kind == "mlp" else bot(lv, s1, s2)
+            else:
+                la, ra = ([1, 0] if torch.rand(1).item() < 0.5 else [0, 1]), ([1, 0] if torch.rand(1).item() < 0.5 else [0, 1])
+        last_ball = loc[0].copy() if valid[0] else None
+        ra, la = clamp(valid[2], loc[2][0], ra), clamp(valid[1], loc[1][0], la)
+        a = cfg.blank_action()
+        a[cfg.RIGHT_ACTION_START:cfg.RIGHT_ACTION_END] = ra; a[cfg.RIGHT_ACTION_END:cfg.LEFT_ACTION_END] = la
+        action = torch.tensor([a], dtype=torch.uint8, device=dev)
+        if last_score is not None:                                    # calculate_timeout_and_frames, main.py:128-135
+            if last_score == (s1, s2):
+                timeout += 1.0
+            else:
+                total += timeout; timeout = 0.0
+        last_score = (s1, s2)
+        if s1 >= cfg.WIN_SCORE or s2 >= cfg.WIN_SCORE or timeout > cfg.TIMEOUT_THRESH or (max_frames and steps >= max_frames):
+            break
+    reward = 0.0 if s1 == s2 else ((s2 - s1) + s2 * mult) / (total / cfg.TIME_SCALER)       # utils.calculate_reward, utils.py:104-109
+    return {"frames": torch.stack(frames), "reward": reward, "steps": steps, "score": (s1, s2)}
 
 
 # ---- checkpoint / resume (utils.py:116-125, ga.py:13-53) -------------------------------------------

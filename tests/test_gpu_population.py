@@ -377,6 +377,29 @@ def test_resume_from_a_reference_checkpoint(ngp, tmp_path):
     tb.engine.close()
 
 
+def test_replay_shows_the_game_the_batched_path_played(ngp):
+    """pickle_inspector.py / evaluate(individual, render=True): the frame-by-frame replay of one individual (explicit-action API +
+    ngp_mlp_forward on the host loop) ends after the same number of env.step calls with the same reward as the fused evaluation of
+    the same game, and keeps one upscaled frame per step (render_game's repeat_upsample 4 x 4)."""
+    from neuro_genetic_pong_self_play_b200.reference_api import Toolbox, replay, repeat_upsample
+    cfg = ngp.Config(POPULATION_SIZE=4)
+    eng = ngp.Engine(cfg, device=0)
+    tb = Toolbox(cfg, eng, seed=3)
+    rng = np.random.RandomState(11)
+    genomes = (rng.standard_normal((4, eng.gene_size)) * 2).astype(np.float32)
+    ref = eng.evaluate(_cuda(genomes), seed=3, generation=0, want_detail=True)
+    for gi, game in ((0, 0), (1, 2), (2, 1)):
+        out = replay(tb, _cuda(genomes[gi]), game=game)
+        assert out["steps"] == int(ref["frames"][gi, game].item())
+        assert out["reward"] == ref["rewards"][gi, game].item()
+        assert tuple(out["frames"].shape) == (out["steps"], 840, 640, 3) and out["frames"].dtype == torch.uint8
+    small = torch.arange(24, dtype=torch.uint8, device="cuda").reshape(2, 4, 3)
+    up = repeat_upsample(small, 2, 3)
+    assert torch.equal(up.cpu(), torch.from_numpy(np.repeat(np.repeat(small.cpu().numpy(), 2, axis=0), 3, axis=1)))
+    assert repeat_upsample(small, 0, 3) is small
+    eng.close()
+
+
 def test_reference_call_surface(ngp, golden, obs_npy):
     """NeuralNetwork(nodes, weights, bias).run, find_stuff(obs), toolbox.evaluate(individual), toolbox.map(toolbox.evaluate, pop)
     read like the reference's call sites (numpy_nn.py:35-50,120-137; utils.py:14-19; main.py:28-66; ga.py:83)."""
