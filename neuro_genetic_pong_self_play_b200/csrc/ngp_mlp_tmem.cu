@@ -20,7 +20,8 @@
 //
 // D^T form as before: M = 128 outputs, N = TN environments (64 or 128: with 128 a genome's weights are streamed once for the
 // 2 x 64 rows of the round-robin stepwise evaluation), K = fan-in (bias handled in the epilogue, so K = 512 exactly for the
-// flagship net).  TMEM: TN accumulator columns + 4 stages x (16 hi + 16 lo) columns = 256 -> two CTAs per SM.
+// flagship net).  TMEM: accumulator columns (TN = 64: two accumulators, main and small terms) + 4 stages x (16 hi + 16 lo)
+// columns = 256 -> two CTAs per SM.
 // Shared-memory traffic per weight byte: one bulk write + one read (2 B/B) instead of ~10 B/B; the tensor core reads only B.
 #include "ngp_internal.h"
 
@@ -32,9 +33,12 @@ constexpr uint32_t TMEM_COLS = 256;
 constexpr int A_THREADS = 256, B_THREADS = 128, THREADS = A_THREADS + B_THREADS + 64;      // + MMA warp + copy warp
 constexpr uint32_t RAW_TILE = KC * TM * 4;                                                 // 8 KB: one packed 128 x 16 weight tile
 
-__host__ __device__ constexpr uint32_t lbo(int TN) { return (uint32_t)TN * 16u + 16u; }            // +16 B: conflict-free stores
-__host__ __device__ constexpr uint32_t tile_b(int TN) { return (KC / 4) * lbo(TN); }               // one of B_hi / B_lo
-__host__ __device__ constexpr uint32_t stage_b(int TN) { return 2 * tile_b(TN); }
+// B stage layout.  TN = 128: two tiles (hi, lo) of 128 rows each.  TN = 64: hi and lo form ONE 128-row tile (rows 64..127 = lo), so
+// that A_hi x [B_hi; B_lo] is a single N = 128 MMA.
+__host__ __device__ constexpr bool folded(int TN) { return TN <= 64; }
+__host__ __device__ constexpr uint32_t lbo(int TN) { return (folded(TN) ? 128u : (uint32_t)TN) * 16u + 16u; }     // +16 B: conflict-free stores
+__host__ __device__ constexpr uint32_t tile_b(int TN) { return folded(TN) ? (64u / 8u) * SBO : (KC / 4) * lbo(TN); }        // byte offset of the lo part
+__host__ __device__ constexpr uint32_t stage_b(int TN) { return folded(TN) ? (KC / 4) * lbo(TN) : 2 * (KC / 4) * lbo(TN); }
 __host__ __device__ constexpr int raw_stages(int TN) { return TN > 64 ? 5 : 8; }           // two CTAs per SM must fit 227 KB
 __host__ __device__ constexpr uint32_t smem_bytes(int TN) { return STAGES * stage_b(TN) + raw_stages(TN) * RAW_TILE + 256 + 128; }
 __host__ __device__ constexpr uint32_t idesc(int TN)
@@ -157,7 +161,9 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = tmem_base_slot;                              // columns [0, TN): accumulator
+    constexpr bool TWO_ACC = TN <= 64;
+    const uint32_t tmem_d = tmem_base_slot;                              // columns [0, TN): accumulator (TWO_ACC: of the hi*hi terms)
+    const uint32_t tmem_d2 = TWO_ACC ? tmem_d + 64 : tmem_d;             // columns [64, 128): accumulator of the lo*hi + hi*lo terms
     const uint32_t tmem_a = tmem_d + 128;                                // columns [128, 256): 4 stages x (16 hi + 16 lo)
     const float *tiles = packed + (size_t)g * per_genome + layer_off + (size_t)ob * NC * (KC * TM);       // this CTA's NC contiguous 8 KB tiles
 
@@ -251,24 +257,40 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
         }
     } else if (warp == (A_THREADS + B_THREADS) / 32) {
         // ------------------------------- MMA warp -------------------------------
+        // One thread issues everything, so its own instruction latency paces the tensor pipe (measured: 90 cycles per MMA with
+        // the descriptors rebuilt each time): the stage loop is unrolled so that every descriptor and TMEM address is the base
+        // plus a compile-time constant.
         if (lane == 0) {
-            for (int c = 0; c < NC; ++c) {
-                const int s = c % STAGES;
-                const uint32_t ph = (c / STAGES) & 1;
-                mbar_wait(bar_a + 8 * s, ph);
-                mbar_wait(bar_b + 8 * s, ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = tmem_a + (uint32_t)(s * 32), a_lo = a_hi + 16;
-                const uint32_t b_hi = smem_base + s * STAGE_B, b_lo = b_hi + TILE_B;
+            const uint64_t desc0 = make_desc(smem_base, LBO);            // + (byte offset >> 4): shared addresses stay below 2^18
+#pragma unroll 1
+            for (int c0 = 0; c0 < NC; c0 += STAGES) {
+                const uint32_t ph = (c0 / STAGES) & 1;
 #pragma unroll
-                for (int j = 0; j < KC / 8; ++j) {
-                    const uint32_t kb = 2 * j * LBO;
-                    umma_ts(tmem_d, a_lo + 8 * j, make_desc(b_hi + kb, LBO), IDESC, (c | j) ? 1u : 0u);       // small terms first
-                    umma_ts(tmem_d, a_hi + 8 * j, make_desc(b_lo + kb, LBO), IDESC, 1u);
-                    umma_ts(tmem_d, a_hi + 8 * j, make_desc(b_hi + kb, LBO), IDESC, 1u);
+                for (int s = 0; s < STAGES; ++s) {
+                    const int c = c0 + s;
+                    if (c < NC) {
+                        mbar_wait(bar_a + 8 * s, ph);
+                        mbar_wait(bar_b + 8 * s, ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_hi = tmem_a + (uint32_t)(s * 32), a_lo = a_hi + 16;
+#pragma unroll
+                        for (int j = 0; j < KC / 8; ++j) {
+                            const uint64_t d_hi = desc0 + (uint64_t)((s * STAGE_B + 2 * j * LBO) >> 4), d_lo = d_hi + (uint64_t)(TILE_B >> 4);
+                            if (TWO_ACC) {
+                                // folded: A_hi x [B_hi; B_lo] is one N = 128 MMA into columns [0, 128) (hi*hi | hi*lo); A_lo x B_hi goes
+                                // on top of the hi*lo half; the epilogue adds the halves
+                                umma_ts(tmem_d, a_hi + 8 * j, d_hi, idesc(128), (c | j) ? 1u : 0u);
+                                umma_ts(tmem_d2, a_lo + 8 * j, d_hi, idesc(64), 1u);
+                            } else {
+                                umma_ts(tmem_d, a_lo + 8 * j, d_hi, IDESC, (c | j) ? 1u : 0u);       // small terms first
+                                umma_ts(tmem_d, a_hi + 8 * j, d_lo, IDESC, 1u);
+                                umma_ts(tmem_d, a_hi + 8 * j, d_hi, IDESC, 1u);
+                            }
+                        }
+                        umma_commit(bar_free + 8 * s);
+                        if (c == NC - 1) umma_commit(bar_done);
+                    }
                 }
-                umma_commit(bar_free + 8 * s);
-                if (c == NC - 1) umma_commit(bar_done);
             }
         }
         __syncwarp();
@@ -295,6 +317,21 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (TWO_ACC) {
+                uint32_t w[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]), "=r"(w[8]), "=r"(w[9]),
+                      "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]), "=r"(w[16]), "=r"(w[17]), "=r"(w[18]),
+                      "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]), "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]),
+                      "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+                    : "r"(taddr + 64) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+            }
             if (o < no) {
                 float *dst = out + ((size_t)g * envs + e0 + col0) * no + o;
                 const int e_left = envs - (e0 + col0);
