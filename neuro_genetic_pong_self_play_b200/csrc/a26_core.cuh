@@ -17,6 +17,7 @@
 //     scanline boundary, which is where WSYNC parks the 6507 anyway.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 // optional event counters for the CPU-side debugging harness (tests/host_sim): no code unless A26_STATS
 #ifdef A26_STATS
@@ -124,12 +125,16 @@ inline void build_decode_table(DecodeTable &t)
 }
 
 // ---- per-environment chip state (TIA + RIOT + paddles + renderer bookkeeping) -----------------
-struct Chip {
-    // TIA level registers
+struct alignas(16) Chip {
+    // The sixteen latches the display loops rewrite all the time, as one aligned 16-byte block: the super-blocks keep them in
+    // four registers (HotLatches) while they run.  Byte order is what hot_* below assume.
+    uint8_t pf0, pf1, pf2, grp0_new;
+    uint8_t grp0_old, grp1_new, grp1_old, enam0;
+    uint8_t enam1, enabl_new, enabl_old, vdelp0;
+    uint8_t vdelp1, vdelbl, resmp0, resmp1;
+    // the other TIA level registers
     uint8_t vsync, vblank, nusiz0, nusiz1, colup0, colup1, colupf, colubk;
-    uint8_t ctrlpf, refp0, refp1, pf0, pf1, pf2, grp0_new, grp0_old;
-    uint8_t grp1_new, grp1_old, enam0, enam1, enabl_new, enabl_old, hmp0, hmp1;
-    uint8_t hmm0, hmm1, hmbl, vdelp0, vdelp1, vdelbl, resmp0, resmp1;
+    uint8_t ctrlpf, refp0, refp1, hmp0, hmp1, hmm0, hmm1, hmbl;
     uint8_t posp0, posp1, posm0, posm1, posbl, suppress, hmove_blank, frame_done;
     uint8_t swcha, swchb, dump_enabled, keyrep, error, pf_dirty, pad1, pad2;   // pf_dirty: pfmask[] is stale (rebuilt on use)
     uint16_t cx, pad3;
@@ -668,6 +673,100 @@ __device__ __forceinline__ bool poke_quick(Chip &s, uint32_t reg, uint32_t v)
     default: return reg > 0x2C;
     }
 #undef A26_QUICK
+}
+
+// ---- register mirror of the sixteen hot latches (Chip bytes 0..15) -------------------------------------------------------
+// One local-memory access costs a lone warp ~30 cycles and every test of poke_quick() a branch; the display-loop super-blocks
+// therefore hold the latch block in four registers, apply a whole iteration's eight writes to a copy with plain ALU
+// operations and only fall back to the memory path when one of the writes would not be quick.
+struct HotLatches { uint32_t w[4]; };
+static_assert(sizeof(Chip) % 16 == 0, "Chip must keep its 16-byte alignment in arrays");
+__device__ __forceinline__ void hot_load(HotLatches &h, const Chip &s)
+{
+#ifdef __CUDA_ARCH__
+    const uint4 v = *reinterpret_cast<const uint4 *>(&s.pf0);
+    h.w[0] = v.x; h.w[1] = v.y; h.w[2] = v.z; h.w[3] = v.w;
+#else
+    memcpy(h.w, &s.pf0, 16);
+#endif
+}
+__device__ __forceinline__ void hot_store(const HotLatches &h, Chip &s)
+{
+#ifdef __CUDA_ARCH__
+    *reinterpret_cast<uint4 *>(&s.pf0) = make_uint4(h.w[0], h.w[1], h.w[2], h.w[3]);
+#else
+    memcpy(&s.pf0, h.w, 16);
+#endif
+}
+__device__ __forceinline__ uint32_t hot_byte(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
+__device__ __forceinline__ uint32_t hot_put(uint32_t w, int i, uint32_t v) { return (w & ~(0xFFu << (8 * i))) | ((v & 0xFFu) << (8 * i)); }
+// The eight latch writes of one iteration of the main display loop, in program order (GRP0, ENAM1, ENAM0, GRP1, PF0, PF1, PF2,
+// ENABL), applied to the mirror by exactly poke_quick()'s rules.  Returns false -- mirror untouched -- when any of them would
+// have to go through the renderer.
+__device__ __forceinline__ bool hot_display_writes(HotLatches &h, uint32_t v_grp0, uint32_t v_enam1, uint32_t v_enam0, uint32_t v_grp1,
+                                                   uint32_t v_pf0, uint32_t v_pf1, uint32_t v_pf2, uint32_t v_enabl)
+{
+    uint32_t n0 = h.w[0], n1 = h.w[1], n2 = h.w[2];
+    const uint32_t w3 = h.w[3];
+    const bool vd0 = (hot_byte(n2, 3) & 1u) != 0, vd1 = (hot_byte(w3, 0) & 1u) != 0, vdbl = (hot_byte(w3, 1) & 1u) != 0;
+    const bool rm0 = (hot_byte(w3, 2) & 2u) != 0, rm1 = (hot_byte(w3, 3) & 2u) != 0;
+    bool ok;
+    {   // GRP0: new latch of player 0, old latch of player 1 takes its new one
+        const uint32_t grp0_new = hot_byte(n0, 3), grp1_new = hot_byte(n1, 1), grp1_old = hot_byte(n1, 2);
+        ok = (vd0 | (v_grp0 == grp0_new)) & (!vd1 | (grp1_old == grp1_new));
+        n0 = hot_put(n0, 3, v_grp0); n1 = hot_put(n1, 2, grp1_new);
+    }
+    ok &= rm1 | (((v_enam1 ^ hot_byte(n2, 0)) & 2u) == 0u);
+    n2 = hot_put(n2, 0, v_enam1);
+    ok &= rm0 | (((v_enam0 ^ hot_byte(n1, 3)) & 2u) == 0u);
+    n1 = hot_put(n1, 3, v_enam0);
+    {   // GRP1: new latch of player 1, old latches of player 0 and the ball take their new ones
+        const uint32_t grp1_new = hot_byte(n1, 1), grp0_old = hot_byte(n1, 0), grp0_new = hot_byte(n0, 3);
+        const uint32_t enabl_new = hot_byte(n2, 1), enabl_old = hot_byte(n2, 2);
+        ok &= (vd1 | (v_grp1 == grp1_new)) & (!vd0 | (grp0_old == grp0_new)) & (!vdbl | (((enabl_old ^ enabl_new) & 2u) == 0u));
+        n1 = hot_put(n1, 1, v_grp1); n1 = hot_put(n1, 0, grp0_new); n2 = hot_put(n2, 2, enabl_new);
+    }
+    ok &= (((v_pf0 ^ hot_byte(n0, 0)) & 0xF0u) == 0u) & (v_pf1 == hot_byte(n0, 1)) & (v_pf2 == hot_byte(n0, 2));
+    n0 = hot_put(n0, 0, v_pf0);
+    ok &= vdbl | (((v_enabl ^ hot_byte(n2, 1)) & 2u) == 0u);
+    n2 = hot_put(n2, 1, v_enabl);
+    if (ok) { h.w[0] = n0; h.w[1] = n1; h.w[2] = n2; }
+    return ok;
+}
+
+// One write to a hot latch, applied to the mirror (the latch always takes the byte, with the old<-new copies of GRP0/GRP1
+// writes).  Returns poke_quick()'s verdict for it: false = something displayed changes, the renderer has to be brought up to
+// the write's time with the state BEFORE it (the caller kept a copy) -- see the event queue of the display-loop super-block.
+template <int REG>
+__device__ __forceinline__ bool hot_write(HotLatches &h, uint32_t v)
+{
+    uint32_t &w0 = h.w[0], &w1 = h.w[1], &w2 = h.w[2];
+    const uint32_t w3 = h.w[3];
+    const bool vd0 = (hot_byte(w2, 3) & 1u) != 0, vd1 = (hot_byte(w3, 0) & 1u) != 0, vdbl = (hot_byte(w3, 1) & 1u) != 0;
+    bool quick;
+    if (REG == 0x0D) { quick = ((v ^ hot_byte(w0, 0)) & 0xF0u) == 0u; w0 = hot_put(w0, 0, v); }
+    else if (REG == 0x0E) { quick = v == hot_byte(w0, 1); w0 = hot_put(w0, 1, v); }
+    else if (REG == 0x0F) { quick = v == hot_byte(w0, 2); w0 = hot_put(w0, 2, v); }
+    else if (REG == 0x1B) {
+        const uint32_t grp1_new = hot_byte(w1, 1);
+        quick = (vd0 | (v == hot_byte(w0, 3))) & (!vd1 | (hot_byte(w1, 2) == grp1_new));
+        w0 = hot_put(w0, 3, v); w1 = hot_put(w1, 2, grp1_new);
+    } else if (REG == 0x1C) {
+        const uint32_t grp0_new = hot_byte(w0, 3), enabl_new = hot_byte(w2, 1);
+        quick = (vd1 | (v == hot_byte(w1, 1))) & (!vd0 | (hot_byte(w1, 0) == grp0_new)) & (!vdbl | (((hot_byte(w2, 2) ^ enabl_new) & 2u) == 0u));
+        w1 = hot_put(w1, 1, v); w1 = hot_put(w1, 0, grp0_new); w2 = hot_put(w2, 2, enabl_new);
+    } else if (REG == 0x1D) {
+        quick = ((hot_byte(w3, 2) & 2u) != 0) | (((v ^ hot_byte(w1, 3)) & 2u) == 0u);
+        w1 = hot_put(w1, 3, v);
+    } else if (REG == 0x1E) {
+        quick = ((hot_byte(w3, 3) & 2u) != 0) | (((v ^ hot_byte(w2, 0)) & 2u) == 0u);
+        w2 = hot_put(w2, 0, v);
+    } else {
+        static_assert(REG == 0x0D || REG == 0x0E || REG == 0x0F || (REG >= 0x1B && REG <= 0x1F), "not a hot latch");
+        quick = vdbl | (((v ^ hot_byte(w2, 1)) & 2u) == 0u);
+        w2 = hot_put(w2, 1, v);
+    }
+    return quick;
 }
 
 // cycles the CPU parks after a WSYNC write that completed at cyc_after

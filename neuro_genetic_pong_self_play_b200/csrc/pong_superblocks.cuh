@@ -44,11 +44,6 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
                                                 uint32_t &sp, uint32_t &pc, uint32_t &fc, uint32_t &fv, uint32_t &nv, uint32_t &zv,
                                                 uint32_t fid, uint32_t &cyc, uint32_t cpu_ls, int max_iters)
 {
-#define A26_SB_POKE(REG_, V_, T_)                                                                              \
-    do {                                                                                                       \
-        const uint32_t pv_ = (V_);                                                                             \
-        if (!poke_quick(s, (REG_), pv_)) tia_poke_changed<VERIFY>(s, T, (REG_), pv_, (T_), cpu_ls, fb);                \
-    } while (0)
     if (sp != 0x1Eu || (fid & 8u)) return false;
     // RAM cells the loop only reads (it writes $84/$85 and, through the stack pointer, TIA latches): loaded once
     const uint32_t w80 = ram.rd32(0x80), wb0 = ram.rd32(0xB0), wb4 = ram.rd32(0xB4), wa4 = ram.rd32(0xA4), wa8 = ram.rd32(0xA8);
@@ -69,6 +64,39 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
     // iteration cost more than the latch reads they save.)
     uint32_t prev_a = 0, prev_b = 0;
     int steady = 0;
+    // The sixteen hot latches live in registers while the block runs (a26_core.cuh: HotLatches).  A write that changes something
+    // displayed does not stop the loop: it is queued -- register, value, cycle stamp and the latch block as it stood before the
+    // write -- and the renderer is brought up to all queued writes in one go when the block is left (nothing inside the loop
+    // reads renderer state: no collision read, no frame end).  Replaying an event restores the latch block of its moment and
+    // calls tia_poke_changed(), i.e. performs exactly the calls the write-by-write order makes, later.  The point is the warp:
+    // every lane's paddles and ball sit on other scanlines, so handled on the spot the renderer runs for one lane at a time at
+    // up to 32 x 10 different iterations of a frame; replayed, lane k's n-th event is handled together with everybody else's.
+    HotLatches hot;
+    hot_load(hot, s);
+    constexpr int MAX_EVENTS = 24;
+    uint32_t ev[MAX_EVENTS][4];                                         // latch words 0..2 before the write, reg | v << 6 | dt << 14
+    int n_ev = 0;
+    const uint32_t t_base = cyc;
+    auto replay = [&]() {
+        for (int k = 0; k < n_ev; ++k) {
+            HotLatches pre;
+            pre.w[0] = ev[k][0]; pre.w[1] = ev[k][1]; pre.w[2] = ev[k][2]; pre.w[3] = hot.w[3];
+            hot_store(pre, s);
+            const uint32_t e = ev[k][3];
+            tia_poke_changed<VERIFY>(s, T, e & 0x3Fu, (e >> 6) & 0xFFu, t_base + (e >> 14), cpu_ls, fb);
+        }
+        n_ev = 0;
+        hot_store(hot, s);
+    };
+#define A26_SB_WRITE(REG_, V_, T_)                                                                             \
+    do {                                                                                                       \
+        const uint32_t pv_ = (V_) & 0xFFu, p0_ = hot.w[0], p1_ = hot.w[1], p2_ = hot.w[2];                     \
+        if (!hot_write<REG_>(hot, pv_)) {                                                                      \
+            ev[n_ev][0] = p0_; ev[n_ev][1] = p1_; ev[n_ev][2] = p2_;                                           \
+            ev[n_ev][3] = (uint32_t)(REG_) | (pv_ << 6) | (((T_) - t_base) << 14);                             \
+            ++n_ev;                                                                                            \
+        }                                                                                                      \
+    } while (0)
     // bounded by the caller (at most one trip of X through its 8-bit range), then back through the dispatcher
     for (int iter = 0; iter < max_iters; ++iter) {
         const uint32_t x1 = (x + 1u) & 0xFFu, x2 = (x + 2u) & 0xFFu;
@@ -90,8 +118,10 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
         if (in1) k += 3u; else { ram.wr(0x85u, x); k += 5u; }
         // ---- CPX #$DC ; BNE $F5E0 ----
         if (x == 0xDCu) {
-            A26_SB_POKE(0x1Bu, v_grp0, t0 + 3u);
-            A26_SB_POKE(0x1Eu, v_enam1, t0 + 16u);
+            if (n_ev > MAX_EVENTS - 2) replay();
+            A26_SB_WRITE(0x1B, v_grp0, t0 + 3u);
+            A26_SB_WRITE(0x1E, v_enam1, t0 + 16u);
+            replay();
             a = in1; y = sel; sp = 0x1Du; fc = 1u; fv = v; nv = zv = 0u;
             cyc = t0 + k + 4u; pc = 0xF63Eu;
             return true;
@@ -132,22 +162,26 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
         steady = (iter > 0 && pack_a == prev_a && pack_b == prev_b) ? steady + 1 : 0;
         prev_a = pack_a; prev_b = pack_b;
         if (steady < 2) {
-            A26_SB_POKE(0x1Bu, v_grp0, t0 + 3u);
-            A26_SB_POKE(0x1Eu, v_enam1, t0 + 16u);
-            A26_SB_POKE(0x1Du, v_enam0, t0 + t_enam0);
-            A26_SB_POKE(0x1Cu, g1, t0 + t_grp1);
-            A26_SB_POKE(0x0Du, v_pf0, t0 + t_pf0);
-            A26_SB_POKE(0x0Eu, v_pf1, t0 + t_pf1);
-            A26_SB_POKE(0x0Fu, v_pf2, t0 + t_pf2);
-            A26_SB_POKE(0x1Fu, v_enabl, t0 + t_enabl);
+            if (!hot_display_writes(hot, v_grp0, v_enam1, v_enam0, g1, v_pf0, v_pf1, v_pf2, v_enabl)) {
+                if (n_ev > MAX_EVENTS - 8) replay();
+                A26_SB_WRITE(0x1B, v_grp0, t0 + 3u);
+                A26_SB_WRITE(0x1E, v_enam1, t0 + 16u);
+                A26_SB_WRITE(0x1D, v_enam0, t0 + t_enam0);
+                A26_SB_WRITE(0x1C, g1, t0 + t_grp1);
+                A26_SB_WRITE(0x0D, v_pf0, t0 + t_pf0);
+                A26_SB_WRITE(0x0E, v_pf1, t0 + t_pf1);
+                A26_SB_WRITE(0x0F, v_pf2, t0 + t_pf2);
+                A26_SB_WRITE(0x1F, v_enabl, t0 + t_enabl);
+            }
         }
         a = r; x = x2; y = g0; fc = c; fv = v; nv = zv = r;
         cyc = t0 + k;
         cyc += wsync_stall(cyc, cpu_ls);
     }
+    replay();
     pc = 0xF621u;
     return true;
-#undef A26_SB_POKE
+#undef A26_SB_WRITE
 }
 
 // The score display loop $F58B-$F5B4, entered at $F58D (the instruction after `STA WSYNC`): one scanline per iteration,
