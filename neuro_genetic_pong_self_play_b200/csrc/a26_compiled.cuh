@@ -29,6 +29,17 @@ enum : int { ERR_UNTRANSLATED = 4 };
 #define A26_SUPERBLOCK_F5CC
 #endif
 
+// After a WSYNC the translated code returns to the dispatcher, where diverged lanes meet again at the scanline boundary.  A
+// warp whose other lanes have all finished their episodes has nobody to meet: it continues at the next instruction (the cycle
+// cap of the dispatcher still bounds a frame).  Measured on a single live lane: -5.4 % per frame; the same shortcut for any warp
+// whose live lanes arrive at the WSYNC together (__activemask() == lanes in the frame) gains nothing (profiles/README.md).
+#define A26_AFTER_WSYNC(PC_, LABEL_)                                                   \
+    do {                                                                               \
+        if (solo && (cyc - start_cyc) < FRAME_CYCLE_CAP) goto LABEL_;                  \
+        pc = (PC_);                                                                    \
+        goto a26_next_;                                                                \
+    } while (0)
+
 #define A26_COMPILED_BLOCKMAP
 #include "generated/pong_core.inc"
 #undef A26_COMPILED_BLOCKMAP
@@ -94,12 +105,14 @@ __device__ __forceinline__ void run_frame_compiled(Chip &s, CpuRegs &r, const Ta
         done = s.error ? 1 : 0;
     }
     const uint32_t start_cyc = cyc;
+    // a warp with a single environment still playing does not wait for anybody (see A26_AFTER_WSYNC)
+    const bool solo = !SYNC && __popc(__ballot_sync(__activemask(), !done)) <= 1;
     for (uint32_t slot = 0;; ++slot) {
         // The display loop's super-block runs all of its iterations in one go only when every lane of the warp that is
         // still inside its frame stands at the loop entry: environments in different game phases reach the loop a few
         // slots apart, and a lane that ran ahead alone would execute the whole loop a second time for the others.
         // (Only a scheduling hint: any iteration count gives the same machine state.)
-        const int sb_iters = __all_sync(__activemask(), done || pc == 0xF621u || pc == 0xF58Du || pc == 0xF5CCu) ? 128 : 1;
+        const int sb_iters = (solo || __all_sync(__activemask(), done || pc == 0xF621u || pc == 0xF58Du || pc == 0xF5CCu)) ? 128 : 1;
         (void)sb_iters;
         if (!done) {
             if ((cyc - start_cyc) >= FRAME_CYCLE_CAP) done = 1;
@@ -120,7 +133,7 @@ __device__ __forceinline__ void run_frame_compiled(Chip &s, CpuRegs &r, const Ta
                     }
                 a26_next_:;
                 }
-                while ((int32_t)(cyc - (cpu_ls + LINE_CYCLES)) >= 0) cpu_ls += LINE_CYCLES;
+                cpu_ls += (cyc - cpu_ls) / LINE_CYCLES * LINE_CYCLES;
             }
         }
         if (SYNC) {

@@ -181,6 +181,24 @@ struct Tables {               // per-CTA shared-memory tables
 
 struct Masks { uint32_t w[5]; };
 
+// Every kernel of this library keeps a thread's Chip in local memory and the Tables in shared memory.  An out-of-line function
+// only sees generic references, and every generic access costs an address-space lookup plus two R2UR for its descriptor; the
+// round trip through the state space lets the compiler emit LDL/STL and LDS with immediate offsets instead.
+#ifdef __CUDA_ARCH__
+template <typename X>
+__device__ __forceinline__ X &as_local(X &g) { return *reinterpret_cast<X *>(__cvta_local_to_generic(__cvta_generic_to_local(&g))); }
+__device__ __forceinline__ Chip &chip_local(Chip &g) { return as_local(g); }
+__device__ __forceinline__ const Tables &tables_shared(const Tables &g)
+{
+    return *reinterpret_cast<const Tables *>(__cvta_shared_to_generic(__cvta_generic_to_shared(&g)));
+}
+#else
+template <typename X>
+__device__ __forceinline__ X &as_local(X &g) { return g; }
+__device__ __forceinline__ Chip &chip_local(Chip &g) { return g; }
+__device__ __forceinline__ const Tables &tables_shared(const Tables &g) { return g; }
+#endif
+
 __device__ __forceinline__ uint32_t rom_byte(const Tables &T, uint32_t addr)
 {
     return reinterpret_cast<const uint8_t *>(T.rom)[addr & 0x7FF];      // little-endian words: one byte load
@@ -258,8 +276,9 @@ __device__ __forceinline__ int copy_offsets(int mode, int c)
     return n == 0xF ? -1 : (int)n * 16;
 }
 
-static __device__ __noinline__ void player_mask(Masks &m, int pos, uint32_t nusiz, uint32_t grp, bool reflect, bool suppress)
+static __device__ __noinline__ void player_mask(Masks &m_, int pos, uint32_t nusiz, uint32_t grp, bool reflect, bool suppress)
 {
+    Masks &m = as_local(m_);
     m.w[0] = m.w[1] = m.w[2] = m.w[3] = m.w[4] = 0;
     if (!grp) return;
     int mode = nusiz & 7;
@@ -274,8 +293,9 @@ static __device__ __noinline__ void player_mask(Masks &m, int pos, uint32_t nusi
         place(m, pat, (start + off) % 160);
     }
 }
-static __device__ __noinline__ void missile_mask(Masks &m, int pos, uint32_t nusiz)
+static __device__ __noinline__ void missile_mask(Masks &m_, int pos, uint32_t nusiz)
 {
+    Masks &m = as_local(m_);
     m.w[0] = m.w[1] = m.w[2] = m.w[3] = m.w[4] = 0;
     int mode = nusiz & 7;
     uint32_t pat = (1u << (1u << ((nusiz >> 4) & 3))) - 1u;
@@ -425,8 +445,10 @@ __device__ __forceinline__ bool render_parts_quick(Chip &s, const Tables &T, con
     }
     return true;
 }
-static __device__ __noinline__ bool render_span_quick(Chip &s, const Tables &T, int x0, int x1, int row_lo, int row_hi)
+static __device__ __noinline__ bool render_span_quick(Chip &s_, const Tables &T_, int x0, int x1, int row_lo, int row_hi)
 {
+    Chip &s = chip_local(s_);
+    const Tables &T = tables_shared(T_);
     const QuickPart part[1] = {{x0, x1, row_lo, row_hi}};
     return render_parts_quick<1>(s, T, part);
 }
@@ -434,8 +456,10 @@ static __device__ __noinline__ bool render_span_quick(Chip &s, const Tables &T, 
 // xc pixels of the target line, all with the current register state.  Only valid while no per-line state is pending
 // (HMOVE blanking, RESPx suppression: both are cleared at the next line start, so the first line would differ).
 // Returns false with nothing changed when the quick rules do not apply.
-static __device__ __noinline__ bool catchup_quick(Chip &s, const Tables &T, int full, int xc)
+static __device__ __noinline__ bool catchup_quick(Chip &s_, const Tables &T_, int full, int xc)
 {
+    Chip &s = chip_local(s_);
+    const Tables &T = tables_shared(T_);
     const int row0 = s.line - YSTART;
     // rows outside the display window have no pixels: clip the row ranges to it (the crop lies inside the window)
     const QuickPart part[3] = {{s.rx, FB_COLS, row0, row0 + 1}, {0, FB_COLS, row0 + 1, row0 + 1 + full}, {0, xc, row0 + 1 + full, row0 + 2 + full}};
@@ -443,8 +467,10 @@ static __device__ __noinline__ bool catchup_quick(Chip &s, const Tables &T, int 
 }
 
 template <bool VERIFY>
-__device__ __noinline__ void render_span(Chip &s, const Tables &T, int x0, int x1, int row, uint8_t *fb_row)
+__device__ __noinline__ void render_span(Chip &s_, const Tables &T_, int x0, int x1, int row, uint8_t *fb_row)
 {
+    Chip &s = chip_local(s_);
+    const Tables &T = tables_shared(T_);
     A26_STAT(2);
     const uint32_t grp0 = (s.vdelp0 & 1) ? s.grp0_old : s.grp0_new, grp1 = (s.vdelp1 & 1) ? s.grp1_old : s.grp1_new;
     const bool bl_on = (((s.vdelbl & 1) ? s.enabl_old : s.enabl_new) & 2) != 0;
@@ -890,8 +916,10 @@ __device__ __forceinline__ void tia_apply(Chip &s, const Tables &T, uint32_t reg
 // which some scanline started.  Returns the number of cycles the CPU stalls (WSYNC).
 // tia_poke_changed: for callers that have already seen poke_quick() fail for this write (and reg != WSYNC).
 template <bool VERIFY>
-__device__ __noinline__ void tia_poke_changed(Chip &s, const Tables &T, uint32_t reg, uint32_t v, uint32_t cyc_after, uint32_t cpu_ls, uint8_t *fb)
+__device__ __noinline__ void tia_poke_changed(Chip &s_, const Tables &T_, uint32_t reg, uint32_t v, uint32_t cyc_after, uint32_t cpu_ls, uint8_t *fb)
 {
+    Chip &s = chip_local(s_);
+    const Tables &T = tables_shared(T_);
     A26_STAT(0);
     tia_apply<VERIFY>(s, T, reg, v, cyc_after, (cyc_after - cpu_ls) % LINE_CYCLES, fb);
 }
@@ -906,8 +934,10 @@ __device__ __forceinline__ uint32_t tia_poke(Chip &s, const Tables &T, uint32_t 
 
 // collision latch read: needs the renderer caught up to the read
 template <bool VERIFY>
-__device__ __noinline__ uint32_t tia_peek_cx(Chip &s, const Tables &T, uint32_t reg, uint32_t cyc_after, uint8_t *fb)
+__device__ __noinline__ uint32_t tia_peek_cx(Chip &s_, const Tables &T_, uint32_t reg, uint32_t cyc_after, uint8_t *fb)
 {
+    Chip &s = chip_local(s_);
+    const Tables &T = tables_shared(T_);
     tia_catchup<VERIFY>(s, T, 3 * (int)(cyc_after - s.tia_ls), fb);
     uint32_t v = (((s.cx >> (2 * reg + 1)) & 1u) << 7) | (((s.cx >> (2 * reg)) & 1u) << 6);
     if (reg == 6) v &= 0x80;
@@ -984,15 +1014,19 @@ __device__ __forceinline__ void clear_obs(Chip &s)
 // device registers behind a run-time address (kept out of line: the inline expansion of every TIA/RIOT
 // path at every indexed access made the translated core several hundred KB of SASS)
 template <bool VERIFY>
-__device__ __noinline__ uint32_t io_read_slow(Chip &s, const Tables &T, uint32_t addr, uint32_t cyc_after, uint32_t dbus, uint8_t *fb)
+__device__ __noinline__ uint32_t io_read_slow(Chip &s_, const Tables &T_, uint32_t addr, uint32_t cyc_after, uint32_t dbus, uint8_t *fb)
 {
+    Chip &s = chip_local(s_);
+    const Tables &T = tables_shared(T_);
     if (addr & 0x80) return riot_peek(s, addr, cyc_after);
     return tia_peek<VERIFY>(s, T, addr, cyc_after, dbus, fb);
 }
 // returns stall cycles | (frame_done << 16)
 template <bool VERIFY>
-__device__ __noinline__ uint32_t io_write_slow(Chip &s, const Tables &T, uint32_t addr, uint32_t v, uint32_t cyc_after, uint32_t cpu_ls, uint8_t *fb)
+__device__ __noinline__ uint32_t io_write_slow(Chip &s_, const Tables &T_, uint32_t addr, uint32_t v, uint32_t cyc_after, uint32_t cpu_ls, uint8_t *fb)
 {
+    Chip &s = chip_local(s_);
+    const Tables &T = tables_shared(T_);
     if (!(addr & 0x1080)) {
         const uint32_t reg = addr & 0x3F;
         if (reg == 0x02) return wsync_stall(cyc_after, cpu_ls);

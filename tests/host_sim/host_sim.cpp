@@ -38,6 +38,7 @@ template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline void __syncthreads() {}
 static inline unsigned __activemask() { return 1u; }
 static inline int __all_sync(unsigned, int v) { return v; }
+static inline unsigned __ballot_sync(unsigned, int v) { return v ? 1u : 0u; }
 static inline int __syncthreads_or(int v) { return v; }
 
 #include "../../neuro_genetic_pong_self_play_b200/csrc/rollout.cuh"

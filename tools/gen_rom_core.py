@@ -32,7 +32,7 @@ BRANCH = {"BPL": ("((nv >> 7) & 1u)", 0), "BMI": ("((nv >> 7) & 1u)", 1), "BVC":
 PAGE_PENALTY = {"abx", "aby", "izy"}          # only for read instructions
 MAX_STRUCTURED_SKIP = 24                      # bytes a structured forward branch may skip
 # dispatch entries tried first, hottest first (dispatches per frame measured with tests/host_sim + A26_STATS)
-HOT_ENTRIES = [0xF5CC, 0xF438, 0xF457, 0xF455, 0xF445]      # with the super-blocks in place (80 dispatches per frame)
+HOT_ENTRIES = []      # with super-blocks and closed-form loops no entry is dispatched more than four times a frame (46 in all)
 # Hand-fused super-blocks (csrc/pong_superblocks.cuh): dispatch entry -> (first byte, last byte + 1, sha1 of the cartridge
 # bytes the fused code was written against).  The hook is only emitted when the ROM still holds exactly those bytes.
 SUPERBLOCKS = {0xF621: (0xF5E0, 0xF63E, "9cf83bee22051baf07f26f6b6fd104e7b6f90ebe"),
@@ -268,7 +268,12 @@ class Gen:
         else:
             reg = static_ea & 0x3F
             if reg == 0x02:                      # WSYNC: park until the end of the scanline, leave the block
-                e(f"cyc += {cyc}u; cyc += wsync_stall(cyc, cpu_ls); pc = 0x{nxt:04X}u; goto a26_next_;")
+                # the dispatcher is where diverged lanes meet again; a warp with a single live lane goes straight on
+                if nxt in self.instrs:
+                    self.goto_targets.add(nxt)
+                    e(f"cyc += {cyc}u; cyc += wsync_stall(cyc, cpu_ls); A26_AFTER_WSYNC(0x{nxt:04X}u, L_{nxt:04X});")
+                else:
+                    e(f"cyc += {cyc}u; cyc += wsync_stall(cyc, cpu_ls); pc = 0x{nxt:04X}u; goto a26_next_;")
                 return True
             e(f"if (!poke_quick(s, 0x{reg:02X}u, {val})) tia_poke_changed<VERIFY>(s, T, 0x{reg:02X}u, {val}, cyc + {cyc}u, cpu_ls, fb);")
             e(f"cyc += {cyc}u + stall_;")

@@ -6,6 +6,7 @@ out=gpurun_out/${tag}_rollout_ab.txt
 {
 python tools/profile_rollout.py --population 1024 --max-frames 300
 python tools/profile_rollout.py --population 1 --max-frames 600
+python tools/profile_rollout.py --population 1 --games 1 --max-frames 600
 python tools/profile_rollout.py --population 2048 --max-frames 300
 python tools/profile_rollout.py --population 16384 --max-frames 100
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras
