@@ -117,15 +117,17 @@ __global__ void env_reset_kernel(const Snapshot *start, Snapshot *envs, int n)
 struct ButtonMap { uint8_t m[16]; };
 
 template <bool VERIFY>
-__global__ void __launch_bounds__(32) env_step_kernel(const Tables *tables, const uint32_t *needed, Snapshot *envs, int n, int core, int players, ButtonMap map,
+__global__ void __launch_bounds__(32) env_step_kernel(const Tables *tables, const uint32_t *needed, Snapshot *envs, int n, int lanes, int core, int players, ButtonMap map,
                                                       const uint8_t *actions, uint8_t *fb, uint8_t *ram_out, float *loc,
                                                       uint8_t *valid, uint8_t *regs, unsigned long long *counters)
 {
     __shared__ Tables T;
     __shared__ uint32_t ram_smem[32 * 32];
     load_tables(T, tables);
-    const int e = blockIdx.x * 32 + threadIdx.x;
-    if (e >= n) return;
+    // `lanes` environments per warp: a small batch is spread over the SMs (stepwise environments follow unrelated action
+    // traces, so the lanes of a warp mostly take turns; one environment per warp runs them side by side)
+    const int e = blockIdx.x * lanes + threadIdx.x;
+    if ((int)threadIdx.x >= lanes || e >= n) return;
     Ram ram{&ram_smem[threadIdx.x]};
     Chip s; CpuRegs r;
     load_snapshot(&envs[e], s, r, ram);
@@ -389,12 +391,15 @@ extern "C" int ngp_env_step_core(ngp_handle *h, int32_t core, const uint8_t *act
     memcpy(bmap.m, h->cfg.button_map, 16);
     if (frames) NGP_CUDA(cudaMemsetAsync(h->d_fb, 0, px, st));
     // with a frame requested every pixel is rendered (verify mode); without, the fused no-framebuffer flavour runs
+    int lanes = (n + 4 * h->sm_count - 1) / (4 * h->sm_count);           // one warp per scheduler before the warps are filled
+    lanes = lanes < 1 ? 1 : (lanes > 32 ? 32 : lanes);
+    const unsigned grid = (unsigned)((n + lanes - 1) / lanes);
     if (frames)
-        env_step_kernel<true><<<(n + 31) / 32, 32, 0, st>>>(h->d_tables, h->d_needed, h->d_envs, n, core ? 1 : 0, h->env_players, bmap, actions, h->d_fb, ram,
-                                                            loc, valid, regs, h->d_counters);
+        env_step_kernel<true><<<grid, 32, 0, st>>>(h->d_tables, h->d_needed, h->d_envs, n, lanes, core ? 1 : 0, h->env_players, bmap, actions, h->d_fb, ram,
+                                                   loc, valid, regs, h->d_counters);
     else
-        env_step_kernel<false><<<(n + 31) / 32, 32, 0, st>>>(h->d_tables, h->d_needed, h->d_envs, n, core ? 1 : 0, h->env_players, bmap, actions, nullptr, ram,
-                                                             loc, valid, regs, h->d_counters);
+        env_step_kernel<false><<<grid, 32, 0, st>>>(h->d_tables, h->d_needed, h->d_envs, n, lanes, core ? 1 : 0, h->env_players, bmap, actions, nullptr, ram,
+                                                    loc, valid, regs, h->d_counters);
     h->launches++;
     NGP_CUDA(cudaGetLastError());
     if (frames) {
