@@ -31,8 +31,9 @@ enum : int { ERR_UNTRANSLATED = 4 };
 
 // After a WSYNC the translated code returns to the dispatcher, where diverged lanes meet again at the scanline boundary.  A
 // warp whose other lanes have all finished their episodes has nobody to meet: it continues at the next instruction (the cycle
-// cap of the dispatcher still bounds a frame).  Measured on a single live lane: -5.4 % per frame; the same shortcut for any warp
-// whose live lanes arrive at the WSYNC together (__activemask() == lanes in the frame) gains nothing (profiles/README.md).
+// cap of the dispatcher still bounds a frame).  Measured on a single live lane: -5.4 % per frame.  The same shortcut for any warp
+// whose live lanes arrive at the WSYNC together gains nothing, and going straight on always costs 7.5 % on evolved generations:
+// meeting at the scanline boundary pays (profiles/README.md, r02s/r02w).
 #define A26_AFTER_WSYNC(PC_, LABEL_)                                                   \
     do {                                                                               \
         if (solo && (cyc - start_cyc) < FRAME_CYCLE_CAP) goto LABEL_;                  \
