@@ -186,11 +186,12 @@ struct Masks { uint32_t w[5]; };
 // round trip through the state space lets the compiler emit LDL/STL and LDS with immediate offsets instead.
 #ifdef __CUDA_ARCH__
 template <typename X>
-__device__ __forceinline__ X &as_local(X &g) { return *reinterpret_cast<X *>(__cvta_local_to_generic(__cvta_generic_to_local(&g))); }
+__device__ __forceinline__ X &as_local(X &g) { __builtin_assume(__isLocal(&g)); return g; }
 __device__ __forceinline__ Chip &chip_local(Chip &g) { return as_local(g); }
 __device__ __forceinline__ const Tables &tables_shared(const Tables &g)
 {
-    return *reinterpret_cast<const Tables *>(__cvta_shared_to_generic(__cvta_generic_to_shared(&g)));
+    __builtin_assume(__isShared(&g));
+    return g;
 }
 #else
 template <typename X>
