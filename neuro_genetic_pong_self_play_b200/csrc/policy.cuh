@@ -80,6 +80,9 @@ __device__ __forceinline__ double det_sigmoid(double z)
 // weight = last column); returns ACT_UP when argmax == 0 (first maximum wins), else ACT_DOWN.
 static __device__ __noinline__ int mlp_small_f64(const Shape &sh, const float *__restrict__ genome, const double x[6], double *out_opt)
 {
+#ifdef __CUDA_ARCH__
+    __builtin_assume(__isLocal(x));                 // the caller's observation vector: LDL instead of generic loads
+#endif
     double cur[FUSED_MAX_WIDTH + 1], nxt[FUSED_MAX_WIDTH + 1];
     const int bias = sh.bias ? 1 : 0;
     for (int i = 0; i < sh.nodes[0]; ++i) cur[i] = x[i];
