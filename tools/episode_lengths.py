@@ -15,6 +15,9 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 gens = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 cfg = ngp.Config(SCHEDULE=ngp.SCHEDULE_ROUND_ROBIN, POPULATION_SIZE=n)
 eng = ngp.Engine(cfg, device=0)
+for kv in sys.argv[3:]:                      # tuning switches for geometry sweeps: rollout_block=64 rollout_nosync=1 ...
+    k, v = kv.split("=")
+    eng.set_option(k, int(v))
 g = eng.init_population(n, seed=1)
 eng.profile_enable(True)
 for gen in range(gens):
