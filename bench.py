@@ -511,6 +511,10 @@ def main():
         for name, fn in (("config1", lambda: short(1, 3, 1)),
                          ("lockstep_capability", lockstep),
                          ("config3", lambda: short(3, 2, 1)),
+                         # the GA workload with every resident lane busy from the first frame: 12 288 genomes x 6 games = 73 728
+                         # environments per GPU, one wave of the 148 x 512 lanes of the CTA-synchronous flavour (full episodes, GA
+                         # step and exchange included) -- north_star's >= 1e9 frames/s target on 8 GPUs without capping episodes
+                         ("ga_large_population", lambda: short(2, 2, 1, population=12288)),
                          ("config4", lambda: short(4, 1, 1)),
                          ("config5", lambda: config5_sweep(ngp, local, world, D))):
             try:
