@@ -317,7 +317,10 @@ def e2e_generations(gen: Generation, steps: int, warmup: int, dist):
         host.copy_(gen.genomes, non_blocking=True)                   # D2H: next generation
         host_fit.copy_(gen.fitness, non_blocking=True)               # D2H: fitness
         host_frames.copy_(fr, non_blocking=True)
-        torch.cuda.synchronize()
+        # the step's results are on the host once THIS stream is done; the record exchange of the generation runs on its side
+        # stream and is consumed a generation later (a device-wide synchronize here would make every rank wait for the slowest
+        # rank's generation in every step, which the exchange was made asynchronous to avoid)
+        torch.cuda.current_stream().synchronize()
         return int(host_frames.sum().item())
 
     for _ in range(warmup):
