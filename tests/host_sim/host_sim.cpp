@@ -208,4 +208,84 @@ void hs_evaluate(void *h, int core, const int32_t *nodes, int n_layers, int bias
     }
 }
 
+// Self-test of the register mirror of the hot latches (csrc/a26_core.cuh: HotLatches, hot_write, hot_display_writes) against
+// poke_quick() + the latch effects of tia_apply(), on RANDOM latch states and values -- including states the cartridge never
+// visits (delayed players and ball, unlocked missiles).  Returns the number of disagreements (0 = none).
+static uint32_t hs_rng(uint64_t &st) { st = st * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(st >> 33); }
+// what the write-by-write order does with one write: poke_quick's verdict, and the latch effect either way
+static bool hs_reference_write(a26::Chip &c, uint32_t reg, uint32_t v)
+{
+    if (a26::poke_quick(c, reg, v)) {
+        if (reg == 0x0E) c.pf1 = (uint8_t)v;          // equal already: poke_quick leaves these two alone
+        if (reg == 0x0F) c.pf2 = (uint8_t)v;
+        return true;
+    }
+    switch (reg) {                                    // tia_apply's latch effects (a26_core.cuh)
+    case 0x0D: c.pf0 = (uint8_t)v; break;
+    case 0x0E: c.pf1 = (uint8_t)v; break;
+    case 0x0F: c.pf2 = (uint8_t)v; break;
+    case 0x1B: c.grp0_new = (uint8_t)v; c.grp1_old = c.grp1_new; break;
+    case 0x1C: c.grp1_new = (uint8_t)v; c.grp0_old = c.grp0_new; c.enabl_old = c.enabl_new; break;
+    case 0x1D: c.enam0 = (uint8_t)v; break;
+    case 0x1E: c.enam1 = (uint8_t)v; break;
+    default: c.enabl_new = (uint8_t)v; break;
+    }
+    return false;
+}
+int hs_hot_latch_selftest(uint64_t seed, int rounds)
+{
+    int bad = 0;
+    uint64_t st = seed * 2 + 1;
+    for (int it = 0; it < rounds; ++it) {
+        a26::Chip c;
+        memset(&c, 0, sizeof(c));
+        uint8_t *b = &c.pf0;
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t r = hs_rng(st);
+            // a few distinct values per byte, so that equal/unequal, enabled/disabled and delayed/undelayed all come up often
+            const uint8_t pool[6] = {0x00, 0xF0, 0x02, 0x01, 0x03, (uint8_t)(r >> 8)};
+            b[i] = pool[r % 6];
+        }
+        uint32_t v[8];
+        for (int i = 0; i < 8; ++i) { const uint32_t r = hs_rng(st); const uint8_t pool[6] = {0x00, 0xF0, 0x02, 0x32, 0xB1, (uint8_t)(r >> 8)}; v[i] = pool[r % 6]; }
+        const uint32_t regs[8] = {0x1B, 0x1E, 0x1D, 0x1C, 0x0D, 0x0E, 0x0F, 0x1F};        // the display loop's program order
+        // (1) one write at a time, every register
+        for (int i = 0; i < 8; ++i) {
+            a26::Chip ref = c;
+            a26::HotLatches h;
+            a26::hot_load(h, c);
+            const bool q_ref = hs_reference_write(ref, regs[i], v[i]);
+            bool q;
+            switch (regs[i]) {
+            case 0x0D: q = a26::hot_write<0x0D>(h, v[i]); break;
+            case 0x0E: q = a26::hot_write<0x0E>(h, v[i]); break;
+            case 0x0F: q = a26::hot_write<0x0F>(h, v[i]); break;
+            case 0x1B: q = a26::hot_write<0x1B>(h, v[i]); break;
+            case 0x1C: q = a26::hot_write<0x1C>(h, v[i]); break;
+            case 0x1D: q = a26::hot_write<0x1D>(h, v[i]); break;
+            case 0x1E: q = a26::hot_write<0x1E>(h, v[i]); break;
+            default: q = a26::hot_write<0x1F>(h, v[i]); break;
+            }
+            a26::Chip got = c;
+            a26::hot_store(h, got);
+            if (q != q_ref || memcmp(&got.pf0, &ref.pf0, 16) != 0) ++bad;
+        }
+        // (2) the whole iteration at once: all-quick or nothing
+        {
+            a26::Chip ref = c;
+            bool all = true;
+            for (int i = 0; i < 8; ++i) all = hs_reference_write(ref, regs[i], v[i]) && all;
+            a26::HotLatches h;
+            a26::hot_load(h, c);
+            const bool ok = a26::hot_display_writes(h, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+            a26::Chip got = c;
+            a26::hot_store(h, got);
+            if (ok != all) ++bad;
+            else if (ok && memcmp(&got.pf0, &ref.pf0, 16) != 0) ++bad;
+            else if (!ok && memcmp(&got.pf0, &c.pf0, 16) != 0) ++bad;                      // refused: the mirror must be untouched
+        }
+    }
+    return bad;
+}
+
 }  // extern "C"

@@ -146,3 +146,12 @@ def test_generic_translation_without_superblocks():
     """-DA26_NO_SUPERBLOCKS: the instruction-by-instruction translation the guards fall back to stays bit-exact too."""
     L, sim = _build_variant("nosb", "-DA26_NO_SUPERBLOCKS")
     _run_fast_against_oracle(L, sim, 300, seed=4)
+
+
+def test_hot_latch_mirror_equals_poke_quick_on_random_states(hs):
+    """csrc/a26_core.cuh keeps the sixteen hot TIA latches of the display loop in registers (HotLatches): hot_write and
+    hot_display_writes must give poke_quick()'s verdict and tia_apply()'s latch bytes for ANY latch state -- the cartridge's own
+    traces never delay a player or unlock a missile, so those rules are exercised here on random states."""
+    L, _ = hs
+    L.hs_hot_latch_selftest.argtypes = [ctypes.c_uint64, ctypes.c_int]
+    assert L.hs_hot_latch_selftest(1, 200000) == 0
