@@ -30,7 +30,14 @@ namespace tmm {
 constexpr int TM = 128, KC = 16, STAGES = 4;
 constexpr uint32_t SBO = 128;
 constexpr uint32_t TMEM_COLS = 256;
-constexpr int A_THREADS = 256, B_THREADS = 128, THREADS = A_THREADS + B_THREADS + 64;      // + MMA warp + copy warp
+constexpr int A_THREADS = 256;
+// B side: the activations of a chunk take ~4 000 cycles from the first load to the published tile (L2 latency behind the weight
+// stream; nothing may be in flight across the warp's fence.proxy.async).  Measured with clock64 in every role
+// (profiles/README.md): four B warps deliver a chunk every ~1 000 cycles and the MMA thread waits for them 36 % of its time.
+// With 64-environment tiles eight B warps hold eight chunks of activations in registers (the prefetch depth) and take turns on the
+// four stages; 128-environment tiles need twice the registers per chunk and stay with four.
+__host__ __device__ constexpr int b_warps(int TN) { return TN > 64 ? 4 : 8; }
+__host__ __device__ constexpr int threads(int TN) { return A_THREADS + 32 * b_warps(TN) + 64; }      // + MMA warp + copy warp
 constexpr uint32_t RAW_TILE = KC * TM * 4;                                                 // 8 KB: one packed 128 x 16 weight tile
 
 // B stage layout.  TN = 128: two tiles (hi, lo) of 128 rows each.  TN = 64: hi and lo form ONE 128-row tile (rows 64..127 = lo), so
@@ -40,7 +47,7 @@ __host__ __device__ constexpr uint32_t lbo(int TN) { return (folded(TN) ? 128u :
 __host__ __device__ constexpr uint32_t tile_b(int TN) { return folded(TN) ? (64u / 8u) * SBO : (KC / 4) * lbo(TN); }        // byte offset of the lo part
 __host__ __device__ constexpr uint32_t stage_b(int TN) { return folded(TN) ? (KC / 4) * lbo(TN) : 2 * (KC / 4) * lbo(TN); }
 __host__ __device__ constexpr int raw_stages(int TN) { return TN > 64 ? 5 : 8; }           // two CTAs per SM must fit 227 KB
-__host__ __device__ constexpr uint32_t smem_bytes(int TN) { return STAGES * stage_b(TN) + raw_stages(TN) * RAW_TILE + 256 + 128; }
+__host__ __device__ constexpr uint32_t smem_bytes(int TN) { return STAGES * stage_b(TN) + raw_stages(TN) * RAW_TILE + 512; }
 __host__ __device__ constexpr uint32_t idesc(int TN)
 {
     // cute::UMMA::InstrDescriptor: D=F32 (bit 4), A=B=TF32 (2 at bits 7, 10), both K-major, N>>3 at 17, M>>4 at 24
@@ -131,11 +138,12 @@ __global__ void __launch_bounds__(256) mlp_pack_layer_kernel(const float *__rest
 }
 
 template <int TN>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(threads(TN), 2)
 mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_t layer_off, const float *__restrict__ in, int envs, int ni, int no,
                       float *__restrict__ out)
 {
     constexpr uint32_t LBO = lbo(TN), TILE_B = tile_b(TN), STAGE_B = stage_b(TN), IDESC = idesc(TN);
+    constexpr int B_WARPS = b_warps(TN), B_THREADS = 32 * B_WARPS;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -147,16 +155,26 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
     // barriers: a_full[s] (4 warps), b_full[s] (4 warps), free[s] (one commit), raw_full[r] (copy thread + bytes), raw_free[r] (4 warps), done
     const uint32_t bar_a = raw_base + NA * RAW_TILE, bar_b = bar_a + 8 * STAGES, bar_free = bar_b + 8 * STAGES, bar_done = bar_free + 8 * STAGES;
     const uint32_t bar_rfull = bar_done + 8, bar_rfree = bar_rfull + 8 * NA;
+    const uint32_t bar_bnext = bar_rfree + 8 * NA;                        // [B_WARPS]: "the stage of your next chunk is free" (one commit)
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 0) {
+    const float *tiles = packed + (size_t)g * per_genome + layer_off + (size_t)ob * NC * (KC * TM);       // this CTA's NC contiguous 8 KB tiles
+    constexpr int COPY_WARP = (A_THREADS + B_THREADS) / 32 + 1;
+    if (warp == COPY_WARP && lane == 0) {
+        // the copy thread sets the barriers up itself and has the first NA weight tiles under way while warp 0 allocates tensor
+        // memory: the ~2 000 cycles a bulk copy takes to arrive are the first thing a CTA waits for
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_a + 8 * s, 4); mbar_init(bar_b + 8 * s, 1); mbar_init(bar_free + 8 * s, 1); }
         for (int r = 0; r < NA; ++r) { mbar_init(bar_rfull + 8 * r, 1); mbar_init(bar_rfree + 8 * r, 4); }
+        for (int w = 0; w < B_WARPS; ++w) mbar_init(bar_bnext + 8 * w, 1);
         mbar_init(bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int c = 0; c < NA && c < NC; ++c) {
+            mbar_expect_tx(bar_rfull + 8 * c, RAW_TILE);
+            bulk_g2s(raw_base + c * RAW_TILE, tiles + (size_t)c * (KC * TM), RAW_TILE, bar_rfull + 8 * c);
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -165,14 +183,13 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
     const uint32_t tmem_d = tmem_base_slot;                              // columns [0, TN): accumulator (TWO_ACC: of the hi*hi terms)
     const uint32_t tmem_d2 = TWO_ACC ? tmem_d + 64 : tmem_d;             // columns [64, 128): accumulator of the lo*hi + hi*lo terms
     const uint32_t tmem_a = tmem_d + 128;                                // columns [128, 256): 4 stages x (16 hi + 16 lo)
-    const float *tiles = packed + (size_t)g * per_genome + layer_off + (size_t)ob * NC * (KC * TM);       // this CTA's NC contiguous 8 KB tiles
 
-    if (warp == (A_THREADS + B_THREADS) / 32 + 1) {
+    if (warp == COPY_WARP) {
         // ------------------------------- copy warp: one bulk copy per chunk, NA chunks ahead -------------------------------
         if (lane == 0) {
-            for (int c = 0; c < NC; ++c) {
+            for (int c = NA; c < NC; ++c) {                              // the first NA are on their way (above)
                 const int r = c % NA;
-                if (c >= NA) mbar_wait(bar_rfree + 8 * r, ((c / NA) - 1) & 1);
+                mbar_wait(bar_rfree + 8 * r, ((c / NA) - 1) & 1);
                 mbar_expect_tx(bar_rfull + 8 * r, RAW_TILE);
                 bulk_g2s(raw_base + r * RAW_TILE, tiles + (size_t)c * (KC * TM), RAW_TILE, bar_rfull + 8 * r);
             }
@@ -230,15 +247,21 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
         // k-unit = (lane >> 3) & 3, row = (lane & 7) + 8 j
         const int cu = (lane >> 3) & 3, rl = lane & 7;
 #pragma unroll 1
-        for (int c = wb; c < NC; c += STAGES) {
+        // Warp wb takes chunks wb, wb + B_WARPS, ...; they all use stage sb = wb % STAGES, which it shares with the warps wb +- STAGES.
+        // A parity wait is only sound for a waiter that sees every completion of its barrier in turn, so "stage free" is not
+        // waited for on the stage's barrier (two warps share it and each would miss every other completion) but on the warp's
+        // own: the MMA thread commits chunk c also to the barrier of the warp that fills this stage next, for chunk c + STAGES.
+        const int sb = wb % STAGES;
+        uint32_t waits = 0;
+        for (int c = wb; c < NC; c += B_WARPS) {
             float4 v[UNITS];
 #pragma unroll
             for (int j = 0; j < UNITS; ++j) {
                 const int row = e0 + rl + 8 * j, k = c * KC + cu * 4;
                 v[j] = (row < envs && k < ni) ? __ldg(reinterpret_cast<const float4 *>(A + (size_t)row * ni + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (c >= STAGES) mbar_wait(bar_free + 8 * wb, ((c / STAGES) - 1) & 1);
-            uint8_t *stage = smem + wb * STAGE_B;
+            if (c >= STAGES) { mbar_wait(bar_bnext + 8 * wb, waits & 1u); ++waits; }
+            uint8_t *stage = smem + sb * STAGE_B;
 #pragma unroll
             for (int j = 0; j < UNITS; ++j) {
                 const int r = rl + 8 * j;
@@ -253,7 +276,7 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_b + 8 * wb);
+            if (lane == 0) mbar_arrive(bar_b + 8 * sb);
         }
     } else if (warp == (A_THREADS + B_THREADS) / 32) {
         // ------------------------------- MMA warp -------------------------------
@@ -262,12 +285,13 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
         // plus a compile-time constant.
         if (lane == 0) {
             const uint64_t desc0 = make_desc(smem_base, LBO);            // + (byte offset >> 4): shared addresses stay below 2^18
+            static_assert(B_WARPS % STAGES == 0, "the unrolled period covers whole turns of the stage ring");
 #pragma unroll 1
-            for (int c0 = 0; c0 < NC; c0 += STAGES) {
-                const uint32_t ph = (c0 / STAGES) & 1;
+            for (int c0 = 0; c0 < NC; c0 += B_WARPS) {
 #pragma unroll
-                for (int s = 0; s < STAGES; ++s) {
-                    const int c = c0 + s;
+                for (int t = 0; t < B_WARPS; ++t) {
+                    const int c = c0 + t, s = t % STAGES;
+                    const uint32_t ph = (uint32_t)((c0 / STAGES + t / STAGES) & 1);
                     if (c < NC) {
                         mbar_wait(bar_a + 8 * s, ph);
                         mbar_wait(bar_b + 8 * s, ph);
@@ -288,6 +312,7 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
                             }
                         }
                         umma_commit(bar_free + 8 * s);
+                        umma_commit(bar_bnext + 8 * ((t + STAGES) % B_WARPS));
                         if (c == NC - 1) umma_commit(bar_done);
                     }
                 }
@@ -316,7 +341,7 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (!TWO_ACC) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");       // two accumulators: both loads in flight, one wait
             if (TWO_ACC) {
                 uint32_t w[32];
                 asm volatile(
@@ -409,10 +434,10 @@ int ngp_mlp_layer_tmem(ngp_handle *h, int l, const float *in, int n_genomes, int
     }
     if (envs > 64) {
         dim3 grid((no + tmm::TM - 1) / tmm::TM, (envs + 127) / 128, n_genomes);
-        tmm::mlp_layer_tmem_kernel<128><<<grid, tmm::THREADS, tmm::smem_bytes(128), st>>>(h->prep_packed, h->prep_per_genome, layer_off, in, envs, ni, no, out);
+        tmm::mlp_layer_tmem_kernel<128><<<grid, tmm::threads(128), tmm::smem_bytes(128), st>>>(h->prep_packed, h->prep_per_genome, layer_off, in, envs, ni, no, out);
     } else {
         dim3 grid((no + tmm::TM - 1) / tmm::TM, 1, n_genomes);
-        tmm::mlp_layer_tmem_kernel<64><<<grid, tmm::THREADS, tmm::smem_bytes(64), st>>>(h->prep_packed, h->prep_per_genome, layer_off, in, envs, ni, no, out);
+        tmm::mlp_layer_tmem_kernel<64><<<grid, tmm::threads(64), tmm::smem_bytes(64), st>>>(h->prep_packed, h->prep_per_genome, layer_off, in, envs, ni, no, out);
     }
     h->launches++;
     NGP_CUDA(cudaGetLastError());
