@@ -97,8 +97,8 @@ __global__ void build_start_states_kernel(const Tables *tables, const uint32_t *
     __shared__ Tables T;
     __shared__ uint32_t ram_smem[32 * 32];
     load_tables(T, tables);
-    const int state = threadIdx.x;
-    if (state >= 2) return;
+    const int state = blockIdx.x;                 // one CTA (one lane of it) per start state: the two scripts diverge from the first frame
+    if (threadIdx.x != 0 || state >= 2) return;
     Ram ram{&ram_smem[threadIdx.x]};
     Chip s; CpuRegs r;
     roll::build_start_state(state, s, r, T, ram, needed);
@@ -314,7 +314,7 @@ extern "C" int ngp_create(const ngp_config *cfg, const uint8_t *rom, int32_t dev
         const uint64_t key = fnv1a64(rom, 2048);
         auto it = g_start_cache.find(key);
         if (it == g_start_cache.end()) {
-            build_start_states_kernel<<<1, 32>>>(h->d_tables, h->d_needed, h->d_start);
+            build_start_states_kernel<<<2, 32>>>(h->d_tables, h->d_needed, h->d_start);
             h->launches++;
             NGP_CUDA(cudaGetLastError());
             std::vector<Snapshot> snap(2);

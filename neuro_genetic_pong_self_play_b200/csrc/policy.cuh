@@ -76,6 +76,37 @@ __device__ __forceinline__ double det_sigmoid(double z)
     return __ddiv_rn(1.0, __dadd_rn(1.0, det_exp(-z)));
 }
 
+// The same network with its three layer widths known at compile time (the reference's default NETWORK_SHAPE [6,2,2] with
+// bias, config.py:30-32): identical operations in identical order -- so identical bits -- but the activations live in registers
+// instead of two 33-entry local arrays and the loops are straight-line code.
+template <int N0, int N1, int N2>
+__device__ __forceinline__ int mlp_fixed_f64(const float *__restrict__ genome, const double *x)
+{
+    double h[N1], out[N2];
+#pragma unroll
+    for (int o = 0; o < N1; ++o) {
+        double z = 0.0;
+#pragma unroll
+        for (int i = 0; i < N0; ++i) z = __dadd_rn(z, __dmul_rn((double)__ldg(&genome[o * (N0 + 1) + i]), x[i]));
+        z = __dadd_rn(z, __dmul_rn((double)__ldg(&genome[o * (N0 + 1) + N0]), 1.0));
+        h[o] = det_sigmoid(z);
+    }
+    const float *w = genome + (N0 + 1) * N1;
+#pragma unroll
+    for (int o = 0; o < N2; ++o) {
+        double z = 0.0;
+#pragma unroll
+        for (int i = 0; i < N1; ++i) z = __dadd_rn(z, __dmul_rn((double)__ldg(&w[o * (N1 + 1) + i]), h[i]));
+        z = __dadd_rn(z, __dmul_rn((double)__ldg(&w[o * (N1 + 1) + N1]), 1.0));
+        out[o] = det_sigmoid(z);
+    }
+    int best = 0;
+#pragma unroll
+    for (int o = 1; o < N2; ++o)
+        if (out[o] > out[best]) best = o;
+    return best == 0 ? ACT_UP : ACT_DOWN;
+}
+
 // NeuralNetwork.run in FP64: weights f32 in reference gene order (row-major (out, in+bias), bias
 // weight = last column); returns ACT_UP when argmax == 0 (first maximum wins), else ACT_DOWN.
 static __device__ __noinline__ int mlp_small_f64(const Shape &sh, const float *__restrict__ genome, const double x[6], double *out_opt)
@@ -83,6 +114,7 @@ static __device__ __noinline__ int mlp_small_f64(const Shape &sh, const float *_
 #ifdef __CUDA_ARCH__
     __builtin_assume(__isLocal(x));                 // the caller's observation vector: LDL instead of generic loads
 #endif
+    if (!out_opt && sh.bias && sh.n_layers == 3 && sh.nodes[0] == 6 && sh.nodes[1] == 2 && sh.nodes[2] == 2) return mlp_fixed_f64<6, 2, 2>(genome, x);
     double cur[FUSED_MAX_WIDTH + 1], nxt[FUSED_MAX_WIDTH + 1];
     const int bias = sh.bias ? 1 : 0;
     for (int i = 0; i < sh.nodes[0]; ++i) cur[i] = x[i];
