@@ -15,6 +15,12 @@
 #pragma once
 #include "a26_core.cuh"
 
+// capacity of the display-loop block's queue of deferred TIA writes; an iteration can add eight, the queue is replayed early
+// when fewer than eight slots are left (tests/test_host_sim.py runs a build with 9 slots, where that happens all the time)
+#ifndef A26_SB_MAX_EVENTS
+#define A26_SB_MAX_EVENTS 24
+#endif
+
 namespace a26 {
 #ifdef __CUDACC__
 
@@ -73,7 +79,7 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
     // up to 32 x 10 different iterations of a frame; replayed, lane k's n-th event is handled together with everybody else's.
     HotLatches hot;
     hot_load(hot, s);
-    constexpr int MAX_EVENTS = 24;
+    constexpr int MAX_EVENTS = A26_SB_MAX_EVENTS;
     uint32_t ev[MAX_EVENTS][4];                                         // latch words 0..2 before the write, reg | v << 6 | dt << 14
     int n_ev = 0;
     const uint32_t t_base = cyc;

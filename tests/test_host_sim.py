@@ -155,3 +155,25 @@ def test_hot_latch_mirror_equals_poke_quick_on_random_states(hs):
     L, _ = hs
     L.hs_hot_latch_selftest.argtypes = [ctypes.c_uint64, ctypes.c_int]
     assert L.hs_hot_latch_selftest(1, 200000) == 0
+
+
+def test_display_loop_event_queue_early_replay():
+    """The display-loop block queues the TIA writes that change the picture and replays them when it is left; when fewer than
+    eight slots are free it replays in the middle of the loop.  With the normal capacity that path is rare: a build with nine
+    slots takes it at every other event, and must still match the oracle frame for frame (RAM and observation)."""
+    L, sim = _build_variant("smallqueue", "-DA26_SB_MAX_EVENTS=9")
+    _run_fast_against_oracle(L, sim, 400, seed=5)
+    # the every-pixel flavour through the same queue: frame buffer, RAM and CPU registers
+    L.hs_env_step.argtypes = [vp, ctypes.c_int] + [vp] * 7
+    rng = np.random.RandomState(6)
+    env = oracle.Atari(); env.reset_to_state(0); L.hs_env_reset(sim, 0)
+    ram = np.zeros(128, np.uint8); fb = np.zeros((210, 160), np.uint8); loc = np.zeros(6); valid = np.zeros(3, np.uint8)
+    regs = np.zeros(8, np.uint8); dig = np.zeros(8, np.uint32)
+    for f in range(200):
+        if f % 5 == 0:
+            act = np.zeros(16, np.uint8); act[0] = act[15] = 1
+            r, l = rng.randint(0, 3), rng.randint(0, 3)
+            act[4] = r == 1; act[5] = r == 2; act[6] = l == 1; act[7] = l == 2
+        ofb = env.step(act)
+        assert L.hs_env_step(sim, 1, P(act), P(ram), P(fb), P(loc), P(valid), P(regs), P(dig)) == 0
+        assert np.array_equal(env.ram, ram) and np.array_equal(env.cpu_regs[:7], regs[:7]) and np.array_equal(ofb, fb), f
