@@ -492,7 +492,7 @@ def main():
             # per-generation breakdown: the rollout kernel on its own CUDA events; what is left of the step is
             # the GA step, the hall-of-fame update and whatever the rank waits for the record exchange (NCCL, asynchronous)
             return {"workload": w["name"], "env_frames_per_s": f / (m * 1e-3), "ms_per_step": m / steps, "rollout_ms_per_step": r / steps,
-                    "ga_hof_exchange_ms_per_step": max(0.0, (m - r) / steps),
+                    "ga_hof_exchange_ms_per_step": max(0.0, (m - r) / steps) if r > 0 else None,       # None: the per-frame driver has no single rollout kernel
                     "frames_per_step": f / steps, "steps": steps, "warmup": warmup, "scaling": w["scaling"]}
 
         def lockstep():
