@@ -12,8 +12,9 @@
 //                     into a deep ring of raw tiles in shared memory (up to 64 KB in flight per CTA, no registers held)
 //   A producers       4 warps, thread = output row (= TMEM lane): 4 x LDS.128 of its row (conflict-free), split  w = hi + lo
 //                     (hi = tf32-truncated), tcgen05.st hi and lo into a 4-stage ring of TMEM columns
-//   B producers       4 warps, warp w owns stage w: activations [env][k] (L2-resident, 16-byte aligned rows) -> registers ->
-//                     hi/lo tiles in shared memory in the canonical no-swizzle K-major core-matrix layout
+//   B producers       8 warps (4 for 128-environment tiles), one chunk each at a time: activations [env][k] (L2-resident,
+//                     16-byte aligned rows) -> registers -> hi/lo tiles in one of four shared-memory stages in the canonical
+//                     no-swizzle K-major core-matrix layout; the warps are the prefetch depth of the activations
 //   MMA warp          per chunk and k-step of 8:  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  ("3xTF32", error ~2^-21) with A from
 //                     TMEM and B from shared memory; tcgen05.commit hands the stage back to both producer groups
 //   epilogue          the A producers (their warp owns the TMEM lanes of its rows): tcgen05.ld, + bias, sigmoid, coalesced stores
@@ -21,7 +22,8 @@
 // D^T form as before: M = 128 outputs, N = TN environments (64 or 128: with 128 a genome's weights are streamed once for the
 // 2 x 64 rows of the round-robin stepwise evaluation), K = fan-in (bias handled in the epilogue, so K = 512 exactly for the
 // flagship net).  TMEM: accumulator columns (TN = 64: two accumulators, main and small terms) + 4 stages x (16 hi + 16 lo)
-// columns = 256 -> two CTAs per SM.
+// columns = 256 -> two CTAs per SM.  Who paces the pipeline was measured with clock64 in every role:
+// profiles/r02zb_mlp_tmem_role_timing.txt.
 // Shared-memory traffic per weight byte: one bulk write + one read (2 B/B) instead of ~10 B/B; the tensor core reads only B.
 #include "ngp_internal.h"
 
@@ -237,22 +239,22 @@ mlp_layer_tmem_kernel(const float *__restrict__ packed, size_t per_genome, size_
         if (pending >= 0) publish(pending);
     } else if (warp < (A_THREADS + B_THREADS) / 32) {
         // ------------------------------- B producers: activations -> hi/lo tiles in shared memory -------------------------------
-        // Warp w fills stage w: chunks w, w + 4, ...  A warp loads a whole chunk (TN rows x 64 bytes), waits for it, splits and
-        // stores it, and only then fences: fence.proxy.async compiles to a MEMBAR that also waits for the thread's outstanding
-        // global loads, so nothing may be in flight across it; the latency is hidden by the other three warps' chunks instead.
+        // A warp loads a whole chunk (TN rows x 64 bytes), waits for it, splits and stores it, and only then fences:
+        // fence.proxy.async compiles to a MEMBAR that also waits for the thread's outstanding global loads, so nothing may be in
+        // flight across it; the latency is hidden by the other warps' chunks instead.
         const int wb = warp - A_THREADS / 32;
         constexpr int UNITS = TN * (KC / 4) / 32;                        // 16-byte units per lane and chunk (8 or 16)
         const float *A = in + (size_t)g * envs * ni;
         // unit u = lane + 32 j: 8 consecutive lanes = 8 consecutive rows of one k-unit (conflict-free 128-byte store rows);
         // k-unit = (lane >> 3) & 3, row = (lane & 7) + 8 j
         const int cu = (lane >> 3) & 3, rl = lane & 7;
-#pragma unroll 1
         // Warp wb takes chunks wb, wb + B_WARPS, ...; they all use stage sb = wb % STAGES, which it shares with the warps wb +- STAGES.
         // A parity wait is only sound for a waiter that sees every completion of its barrier in turn, so "stage free" is not
         // waited for on the stage's barrier (two warps share it and each would miss every other completion) but on the warp's
         // own: the MMA thread commits chunk c also to the barrier of the warp that fills this stage next, for chunk c + STAGES.
         const int sb = wb % STAGES;
         uint32_t waits = 0;
+#pragma unroll 1
         for (int c = wb; c < NC; c += B_WARPS) {
             float4 v[UNITS];
 #pragma unroll
