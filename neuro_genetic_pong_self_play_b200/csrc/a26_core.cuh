@@ -16,6 +16,7 @@
 //   * The instruction loop is scanline-synchronous: all lanes of a warp re-converge at every
 //     scanline boundary, which is where WSYNC parks the 6507 anyway.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -708,6 +709,11 @@ __device__ __forceinline__ bool poke_quick(Chip &s, uint32_t reg, uint32_t v)
 // operations and only fall back to the memory path when one of the writes would not be quick.
 struct HotLatches { uint32_t w[4]; };
 static_assert(sizeof(Chip) % 16 == 0, "Chip must keep its 16-byte alignment in arrays");
+static_assert(offsetof(Chip, pf0) == 0 && offsetof(Chip, pf1) == 1 && offsetof(Chip, pf2) == 2 && offsetof(Chip, grp0_new) == 3 &&
+              offsetof(Chip, grp0_old) == 4 && offsetof(Chip, grp1_new) == 5 && offsetof(Chip, grp1_old) == 6 && offsetof(Chip, enam0) == 7 &&
+              offsetof(Chip, enam1) == 8 && offsetof(Chip, enabl_new) == 9 && offsetof(Chip, enabl_old) == 10 && offsetof(Chip, vdelp0) == 11 &&
+              offsetof(Chip, vdelp1) == 12 && offsetof(Chip, vdelbl) == 13 && offsetof(Chip, resmp0) == 14 && offsetof(Chip, resmp1) == 15,
+              "hot_byte()/hot_put() index the latch block by these byte positions");
 __device__ __forceinline__ void hot_load(HotLatches &h, const Chip &s)
 {
 #ifdef __CUDA_ARCH__

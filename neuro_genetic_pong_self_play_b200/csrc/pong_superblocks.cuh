@@ -80,6 +80,8 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
     HotLatches hot;
     hot_load(hot, s);
     constexpr int MAX_EVENTS = A26_SB_MAX_EVENTS;
+    static_assert(MAX_EVENTS >= 9, "an iteration can queue eight writes");
+    static_assert(128 * 2 * LINE_CYCLES + 2 * LINE_CYCLES < (1 << 18), "an event's cycle stamp is stored as an 18-bit offset from the block's entry (the caller runs at most 128 iterations)");
     uint32_t ev[MAX_EVENTS][4];                                         // latch words 0..2 before the write, reg | v << 6 | dt << 14
     int n_ev = 0;
     const uint32_t t_base = cyc;
