@@ -24,6 +24,15 @@
 namespace a26 {
 #ifdef __CUDACC__
 
+// WSYNC at the end of a loop iteration without a division: `rel` = cycles between the start of a scanline and the iteration's
+// first cycle (0 from the second iteration on: the previous WSYNC aligned it), k = length of the iteration, at most three lines.
+__device__ __forceinline__ uint32_t sb_wsync(uint32_t &rel, uint32_t k)
+{
+    const uint32_t c = rel + k;                    // cycles since that line start; the CPU parks until the next multiple of 76
+    rel = 0u;
+    return c <= LINE_CYCLES ? LINE_CYCLES - c : (c <= 2u * LINE_CYCLES ? 2u * LINE_CYCLES - c : 3u * LINE_CYCLES - c);
+}
+
 // SBC with carry set (the loop always executes SEC first), binary mode: result byte, carry, overflow
 __device__ __forceinline__ void sb_sbc(uint32_t acc, uint32_t m, uint32_t &r, uint32_t &c, uint32_t &v)
 {
@@ -105,6 +114,7 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
             ++n_ev;                                                                                            \
         }                                                                                                      \
     } while (0)
+    uint32_t rel = (cyc - cpu_ls) % LINE_CYCLES;                        // see sb_wsync
     // bounded by the caller (at most one trip of X through its 8-bit range), then back through the dispatcher
     for (int iter = 0; iter < max_iters; ++iter) {
         const uint32_t x1 = (x + 1u) & 0xFFu, x2 = (x + 2u) & 0xFFu;
@@ -183,8 +193,7 @@ __device__ __forceinline__ bool superblock_f621(Chip &s, const Tables &T, Ram ra
             }
         }
         a = r; x = x2; y = g0; fc = c; fv = v; nv = zv = r;
-        cyc = t0 + k;
-        cyc += wsync_stall(cyc, cpu_ls);
+        cyc = t0 + k + sb_wsync(rel, k);                                // k <= 153: within three lines of the iteration's line start
     }
     replay();
     pc = 0xF621u;
@@ -227,6 +236,7 @@ __device__ __forceinline__ bool superblock_f58d(Chip &s, const Tables &T, Ram ra
         tia_poke_changed<VERIFY>(s, T, 0x0Eu, pv, t, cpu_ls, fb);
         refresh_zone();
     };
+    uint32_t rel = (cyc - cpu_ls) % LINE_CYCLES;
     for (int iter = 0; iter < max_iters; ++iter) {
         const uint32_t t0 = cyc;
         const uint32_t m1 = rom_byte(T, q5 + y), m2 = rom_byte(T, q9 + y), m3 = rom_byte(T, q7 + y), m4 = rom_byte(T, qb + y);
@@ -250,8 +260,7 @@ __device__ __forceinline__ bool superblock_f58d(Chip &s, const Tables &T, Ram ra
             }
         }
         k += 3u + 3u;                              // taken branch (same page) + STA WSYNC
-        cyc = t0 + k;
-        cyc += wsync_stall(cyc, cpu_ls);
+        cyc = t0 + k + sb_wsync(rel, k);           // k <= 77
     }
     ram.wr(0x87u, scratch);
     pc = 0xF58Du;
@@ -267,6 +276,7 @@ template <bool VERIFY>
 __device__ __forceinline__ bool superblock_f5cc(Chip &s, const Tables &T, uint8_t *fb, uint32_t &a, uint32_t &y, uint32_t &pc, uint32_t &nv,
                                                 uint32_t &zv, uint32_t &cyc, uint32_t cpu_ls, int max_iters)
 {
+    uint32_t rel = (cyc - cpu_ls) % LINE_CYCLES;
     for (int iter = 0; iter < max_iters; ++iter) {
         const uint32_t t0 = cyc;
         y = (y - 1u) & 0xFFu;                              // DEY
@@ -278,8 +288,7 @@ __device__ __forceinline__ bool superblock_f5cc(Chip &s, const Tables &T, uint8_
             for (int i = 0; i < 8; ++i)
                 if (!poke_quick(s, regs[i], 0u)) tia_poke_changed<VERIFY>(s, T, regs[i], 0u, t0 + 10u + 3u * (uint32_t)i, cpu_ls, fb);
         }
-        cyc = t0 + 34u;                                    // 2 + 3 + 2 + 8 * 3 + 3 (STY WSYNC)
-        cyc += wsync_stall(cyc, cpu_ls);
+        cyc = t0 + 34u + sb_wsync(rel, 34u);               // 2 + 3 + 2 + 8 * 3 + 3 (STY WSYNC)
     }
     pc = 0xF5CCu;
     return true;
